@@ -1,0 +1,505 @@
+// extern "C" surface of libptb200.so (declared in include/ptb200.h).  Thin: argument validation, error
+// plumbing, workspace management and launch sequencing; the work is in the *_kernels.cu files.
+#include <cerrno>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <string>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <vector>
+
+#include "pt_host.h"
+
+namespace ptb200 {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof g_err, "%s: CUDA error %d (%s)", what, static_cast<int>(e), cudaGetErrorString(e));
+    cudaGetLastError();  // clear the sticky-less error state
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return PTB200_ENODEV;
+    return static_cast<int>(e);
+}
+
+namespace {
+
+std::mutex g_cfg_mu;
+PtParams g_legacy = {16, 16, 1, 5, 8, 8, 7, 12.0f, 0, 0};  // src/common.h:4-6,10; render.cpp:141,194; rt_helper.h:776
+
+int64_t total_paths(const PtParams &p) { return static_cast<int64_t>(p.width) * p.height * 4 * p.samples; }
+
+int check_params(const PtParams *p, const char *who) {
+    if (p == nullptr)
+        return fail(PTB200_EINVAL, "%s: params is NULL", who);
+    if (p->width < 1 || p->height < 1 || p->samples < 1)
+        return fail(PTB200_EINVAL, "%s: width/height/samples must be >= 1 (got %d x %d x %d)", who, p->width, p->height, p->samples);
+    if (p->depth < 1)
+        return fail(PTB200_EINVAL, "%s: depth must be >= 1 (got %d)", who, p->depth);
+    if (p->sphere_count < 1 || p->sphere_count > 1024)
+        return fail(PTB200_EINVAL, "%s: sphere_count must be in [1, 1024] for the brute-force kernel (got %d)", who, p->sphere_count);
+    if (p->sphere_stride < p->sphere_count)
+        return fail(PTB200_EINVAL, "%s: sphere_stride (%d) < sphere_count (%d)", who, p->sphere_stride, p->sphere_count);
+    return PTB200_OK;
+}
+
+int check_device(const char *who) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        return fail(PTB200_ENODEV, "%s: no CUDA device (this library has no CPU fallback)", who);
+    }
+    return PTB200_OK;
+}
+
+// ---- per-device workspace arena (grown on demand) ----------------------------------------------------
+struct Workspace {
+    PtArena *arena = nullptr;
+    size_t capacity = 0;
+};
+Workspace g_ws[64];
+std::mutex g_ws_mu;
+
+// Returns an arena with at least `bytes` free in one block; recreates (after a device sync) when too small.
+int workspace(size_t bytes, PtArena **out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return fail_cuda(e, "workspace");
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    Workspace &w = g_ws[dev & 63];
+    if (w.arena == nullptr || ptb200_arena_largest_free(w.arena) < bytes) {
+        if (w.arena != nullptr) {
+            if (ptb200_arena_in_use(w.arena) != 0)
+                return fail(PTB200_ENOMEM, "workspace: arena too small (%zu needed) while still in use", bytes);
+            cudaDeviceSynchronize();
+            ptb200_arena_destroy(w.arena);
+            w.arena = nullptr;
+        }
+        const size_t cap = bytes + (bytes >> 3) + (1u << 20);
+        int rc = ptb200_arena_create(cap, &w.arena);
+        if (rc != PTB200_OK)
+            return rc;
+        w.capacity = cap;
+    }
+    *out = w.arena;
+    return PTB200_OK;
+}
+
+}  // namespace
+}  // namespace ptb200
+
+using namespace ptb200;
+
+extern "C" {
+
+void ptb200_default_params(PtParams *p) {
+    if (p == nullptr)
+        return;
+    const PtParams d = {16, 16, 1, 5, 8, 8, 7, 12.0f, 0, 0};
+    *p = d;
+}
+
+int ptb200_abi_version(void) { return PTB200_ABI_VERSION; }
+
+const char *ptb200_last_error(void) { return g_err; }
+
+int ptb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ptb200_set_legacy_config(const PtParams *p) {
+    int rc = check_params(p, "ptb200_set_legacy_config");
+    if (rc != PTB200_OK)
+        return rc;
+    const int64_t n = total_paths(*p);
+    // DataFormatCheck, src/render.cpp:68-73 (8 cores, 64-ray tiles, double buffered)
+    if (n % 8 != 0 || (n / 8) % 128 != 0)
+        return fail(PTB200_EINVAL, "ptb200_set_legacy_config: N = W*H*S*4 = %lld violates the reference's tiling rule (N %% 8 == 0, N/8 %% 128 == 0)",
+                    static_cast<long long>(n));
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    g_legacy = *p;
+    return PTB200_OK;
+}
+
+void ptb200_get_legacy_config(PtParams *p) {
+    if (p == nullptr)
+        return;
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    *p = g_legacy;
+}
+
+int render_do_ex(const PtParams *p, void *stream, const uint8_t *rays, const uint8_t *spheres, uint8_t *colors, int64_t first,
+                 int64_t count) {
+    int rc = check_params(p, "render_do_ex");
+    if (rc != PTB200_OK)
+        return rc;
+    const int64_t n = total_paths(*p);
+    if (count < 0)
+        count = n - first;
+    if (first < 0 || first + count > n)
+        return fail(PTB200_EINVAL, "render_do_ex: slice [%lld, %lld) outside [0, %lld)", static_cast<long long>(first),
+                    static_cast<long long>(first + count), static_cast<long long>(n));
+    if (count == 0)
+        return PTB200_OK;
+    if (rays == nullptr || spheres == nullptr || colors == nullptr)
+        return fail(PTB200_EINVAL, "render_do_ex: NULL buffer");
+    if ((rc = check_device("render_do_ex")) != PTB200_OK)
+        return rc;
+    cudaError_t e = trace_paths(static_cast<cudaStream_t>(stream), *p, reinterpret_cast<const float *>(rays),
+                                reinterpret_cast<const float *>(spheres), reinterpret_cast<float *>(colors), n, first, count, nullptr);
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "render_do_ex");
+}
+
+void render_do(uint32_t blockDim, void *l2ctrl, void *stream, uint8_t *rays, uint8_t *spheres, uint8_t *colors) {
+    (void)blockDim;
+    (void)l2ctrl;
+    PtParams p;
+    ptb200_get_legacy_config(&p);
+    int rc = render_do_ex(&p, stream, rays, spheres, colors, 0, -1);
+    if (rc != PTB200_OK)  // CHECK_ACL style, src/data_utils.h:41-47: report and carry on
+        fprintf(stderr, "%s:%d ptb200 error:%d %s\n", __FILE__, __LINE__, rc, g_err);
+}
+
+void render(uint8_t *rays, uint8_t *spheres, uint8_t *colors) {
+    render_do(8, nullptr, nullptr, rays, spheres, colors);
+    cudaError_t e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess)
+        fprintf(stderr, "%s:%d ptb200 error:%d %s\n", __FILE__, __LINE__, static_cast<int>(e), cudaGetErrorString(e));
+}
+
+int ptb200_gen_rays(const PtParams *p, void *stream, const double *uniforms, uint64_t seed, int32_t x0, int32_t x1, float *rays) {
+    int rc = check_params(p, "ptb200_gen_rays");
+    if (rc != PTB200_OK)
+        return rc;
+    if (x0 < 0 || x1 > p->width || x0 > x1)
+        return fail(PTB200_EINVAL, "ptb200_gen_rays: columns [%d, %d) outside [0, %d)", x0, x1, p->width);
+    if (x0 == x1)
+        return PTB200_OK;
+    if (rays == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_gen_rays: NULL output");
+    if ((rc = check_device("ptb200_gen_rays")) != PTB200_OK)
+        return rc;
+    const int64_t per_col = static_cast<int64_t>(p->height) * 4 * p->samples;
+    cudaError_t e = gen_rays(static_cast<cudaStream_t>(stream), *p, uniforms, seed, x0 * per_col, (x1 - x0) * per_col, rays);
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_gen_rays");
+}
+
+int ptb200_resolve(const PtParams *p, void *stream, const float *colors, int32_t x0, int32_t x1, uint8_t *image) {
+    int rc = check_params(p, "ptb200_resolve");
+    if (rc != PTB200_OK)
+        return rc;
+    if (x0 < 0 || x1 > p->width || x0 > x1)
+        return fail(PTB200_EINVAL, "ptb200_resolve: columns [%d, %d) outside [0, %d)", x0, x1, p->width);
+    if (x0 == x1)
+        return PTB200_OK;
+    if (colors == nullptr || image == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_resolve: NULL buffer");
+    if ((rc = check_device("ptb200_resolve")) != PTB200_OK)
+        return rc;
+    const int64_t n = total_paths(*p);
+    const int64_t pix0 = static_cast<int64_t>(x0) * p->height;
+    const int64_t npix = static_cast<int64_t>(x1 - x0) * p->height;
+    cudaError_t e = resolve_pixels(static_cast<cudaStream_t>(stream), *p, colors + pix0 * 4 * p->samples, n, pix0, npix, image, x0, x1 - x0);
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_resolve");
+}
+
+int ptb200_render_image(const PtParams *p, void *stream_, const uint8_t *spheres, const double *uniforms, uint64_t seed, int32_t x0,
+                        int32_t x1, uint8_t *image, uint64_t *stats) {
+    int rc = check_params(p, "ptb200_render_image");
+    if (rc != PTB200_OK)
+        return rc;
+    if (x0 < 0 || x1 > p->width || x0 > x1)
+        return fail(PTB200_EINVAL, "ptb200_render_image: columns [%d, %d) outside [0, %d)", x0, x1, p->width);
+    if (x0 == x1)
+        return PTB200_OK;
+    if (spheres == nullptr || image == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_render_image: NULL buffer");
+    if ((rc = check_device("ptb200_render_image")) != PTB200_OK)
+        return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t spp = 4LL * p->samples;
+    const int64_t pix_begin = static_cast<int64_t>(x0) * p->height, pix_end = static_cast<int64_t>(x1) * p->height;
+    // Tile = whole pixels, about 8 Mi paths: rays (24 B) + colours (12 B) per path stay L2/HBM resident between
+    // the three kernels of a tile and never travel to the host.
+    const int64_t target_paths = 8LL << 20;
+    int64_t tile_pix = target_paths / spp;
+    if (tile_pix < 1)
+        tile_pix = 1;
+    if (tile_pix > pix_end - pix_begin)
+        tile_pix = pix_end - pix_begin;
+    const int64_t tile_paths = tile_pix * spp;
+    PtArena *arena = nullptr;
+    const size_t ray_bytes = sizeof(float) * 6 * static_cast<size_t>(tile_paths), col_bytes = sizeof(float) * 3 * static_cast<size_t>(tile_paths);
+    if ((rc = workspace(ray_bytes + col_bytes + 4096, &arena)) != PTB200_OK)
+        return rc;
+    float *rays = static_cast<float *>(ptb200_arena_alloc(arena, ray_bytes));
+    float *cols = static_cast<float *>(ptb200_arena_alloc(arena, col_bytes));
+    if (rays == nullptr || cols == nullptr) {
+        ptb200_arena_free(arena, rays);
+        ptb200_arena_free(arena, cols);
+        return PTB200_ENOMEM;
+    }
+    PtParams tp = *p;
+    cudaError_t e = cudaSuccess;
+    if (stats != nullptr)
+        e = cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), stream);
+    for (int64_t q = pix_begin; q < pix_end && e == cudaSuccess; q += tile_pix) {
+        const int64_t npix = (pix_end - q < tile_pix) ? pix_end - q : tile_pix;
+        const int64_t m = npix * spp;
+        const double *u = uniforms ? uniforms + 2 * (q - pix_begin) * spp : nullptr;
+        if ((e = gen_rays(stream, *p, u, seed, q * spp, m, rays)) != cudaSuccess)
+            break;
+        // the tile is its own m-path problem for the trace kernel
+        if ((e = trace_paths(stream, tp, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m,
+                             stats ? reinterpret_cast<unsigned long long *>(stats) + 1 : nullptr)) != cudaSuccess)
+            break;
+        if ((e = resolve_pixels(stream, *p, cols, m, q, npix, image, x0, x1 - x0)) != cudaSuccess)
+            break;
+    }
+    const unsigned long long total = static_cast<unsigned long long>((pix_end - pix_begin) * spp);
+    if (e == cudaSuccess && stats != nullptr)
+        e = cudaMemcpyAsync(stats, &total, sizeof total, cudaMemcpyHostToDevice, stream);  // drained by the sync below
+    // Stream-ordered reuse: the buffers go back to the arena once the work queued above has drained.
+    cudaError_t es = cudaStreamSynchronize(stream);
+    ptb200_arena_free(arena, rays);
+    ptb200_arena_free(arena, cols);
+    if (e == cudaSuccess)
+        e = es;
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_render_image");
+}
+
+int ptb200_render_host(const PtParams *p, const float *rays_host, const float *spheres_host, float *colors_host) {
+    int rc = check_params(p, "ptb200_render_host");
+    if (rc != PTB200_OK)
+        return rc;
+    if (rays_host == nullptr || spheres_host == nullptr || colors_host == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_render_host: NULL buffer");
+    if ((rc = check_device("ptb200_render_host")) != PTB200_OK)
+        return rc;
+    const int64_t n = total_paths(*p);
+    const size_t sph_bytes = sizeof(float) * 10 * static_cast<size_t>(p->sphere_stride);
+    const size_t sph_alloc = sph_bytes < 512 ? 512 : sph_bytes;
+    // Chunked so that the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap
+    // (three engines, three streams).  With pinned host memory the copies are truly asynchronous.
+    constexpr int kStreams = 3;
+    int64_t chunk = 4LL << 20;  // paths per chunk: 96 MiB in, 48 MiB out
+    if (chunk > n)
+        chunk = n;
+    const int nbuf = static_cast<int>((n + chunk - 1) / chunk < kStreams ? (n + chunk - 1) / chunk : kStreams);
+    PtArena *arena = nullptr;
+    const size_t per_buf = sizeof(float) * 9 * static_cast<size_t>(chunk) + 1024;
+    if ((rc = workspace(per_buf * nbuf + sph_alloc + 4096, &arena)) != PTB200_OK)
+        return rc;
+    float *d_sph = static_cast<float *>(ptb200_arena_alloc(arena, sph_alloc));
+    float *d_buf[kStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    bool ok = d_sph != nullptr;
+    for (int b = 0; b < nbuf && ok; b++) {
+        d_buf[b] = static_cast<float *>(ptb200_arena_alloc(arena, per_buf));
+        ok = d_buf[b] != nullptr;
+        if (ok && (e = cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking)) != cudaSuccess)
+            ok = false;
+    }
+    cudaEvent_t sph_ready = nullptr;
+    if (ok && (e = cudaEventCreateWithFlags(&sph_ready, cudaEventDisableTiming)) != cudaSuccess)
+        ok = false;
+    if (ok) {
+        e = cudaMemcpyAsync(d_sph, spheres_host, sph_bytes, cudaMemcpyHostToDevice, st[0]);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(sph_ready, st[0]);
+        for (int b = 1; b < nbuf && e == cudaSuccess; b++)
+            e = cudaStreamWaitEvent(st[b], sph_ready, 0);
+        PtParams cp = *p;
+        int k = 0;
+        for (int64_t a = 0; a < n && e == cudaSuccess; a += chunk, k++) {
+            const int64_t m = (n - a < chunk) ? n - a : chunk;
+            const int b = k % nbuf;
+            float *d_rays = d_buf[b], *d_cols = d_buf[b] + 6 * chunk;
+            for (int c = 0; c < 6 && e == cudaSuccess; c++)
+                e = cudaMemcpyAsync(d_rays + c * m, rays_host + c * n + a, sizeof(float) * m, cudaMemcpyHostToDevice, st[b]);
+            if (e == cudaSuccess)
+                e = trace_paths(st[b], cp, d_rays, d_sph, d_cols, m, 0, m, nullptr);
+            for (int c = 0; c < 3 && e == cudaSuccess; c++)
+                e = cudaMemcpyAsync(colors_host + c * n + a, d_cols + c * m, sizeof(float) * m, cudaMemcpyDeviceToHost, st[b]);
+        }
+    }
+    for (int b = 0; b < nbuf; b++)
+        if (st[b] != nullptr) {
+            cudaError_t es = cudaStreamSynchronize(st[b]);
+            if (e == cudaSuccess)
+                e = es;
+            cudaStreamDestroy(st[b]);
+        }
+    if (sph_ready != nullptr)
+        cudaEventDestroy(sph_ready);
+    ptb200_arena_free(arena, d_sph);
+    for (int b = 0; b < nbuf; b++)
+        ptb200_arena_free(arena, d_buf[b]);
+    if (!ok && e == cudaSuccess)
+        return PTB200_ENOMEM;
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_render_host");
+}
+
+// ---- host helpers -------------------------------------------------------------------------------------
+
+int ptb200_mt19937_uniforms(uint32_t seed, uint64_t skip, uint64_t n, double *out) {
+    if (out == nullptr && n > 0)
+        return fail(PTB200_EINVAL, "ptb200_mt19937_uniforms: NULL output");
+    // NumPy legacy RandomState (scripts/gen_data.py:438): init_genrand(seed), doubles by genrand_res53.
+    uint32_t mt[624];
+    mt[0] = seed;
+    for (int i = 1; i < 624; i++)
+        mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + static_cast<uint32_t>(i);
+    int pos = 624;
+    auto next = [&]() -> uint32_t {
+        if (pos >= 624) {
+            for (int k = 0; k < 624; k++) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            pos = 0;
+        }
+        uint32_t y = mt[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    };
+    for (uint64_t i = 0; i < 2 * skip; i++)
+        (void)next();
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t a = next() >> 5, b = next() >> 6;
+        out[i] = (static_cast<double>(a) * 67108864.0 + static_cast<double>(b)) / 9007199254740992.0;
+    }
+    return PTB200_OK;
+}
+
+int ptb200_default_scene(float *out) {
+    if (out == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_default_scene: NULL output");
+    // scripts/gen_data.py:94-102: radius, centre, emission, colour; float64 table, radius squared, cast (:109,:127)
+    static const double tbl[8][10] = {
+        {1e5, 1e5 + 1, 40.8, 81.6, 0, 0, 0, 0.435, 0.376, 0.667},  {1e5, -1e5 + 99, 40.8, 81.6, 0, 0, 0, 0.667, 0.129, 0.086},
+        {1e5, 50, 40.8, 1e5, 0, 0, 0, 0.270, 0.725, 0.486},        {1e5, 50, 40.8, -1e5 + 170, 0, 0, 0, 0, 0, 0},
+        {1e5, 50, 1e5, 81.6, 0, 0, 0, 0.5, 0.5, 0.5},              {1e5, 50, -1e5 + 81.6, 81.6, 0, 0, 0, 0.141, 0.408, 0.635},
+        {16.5, 27, 16.5, 47, 0, 0, 0, 0.999, 0.999, 0.999},        {600, 50, 681.6 - 0.27, 81.6, 12, 12, 12, 0, 0, 0}};
+    memset(out, 0, 128 * sizeof(float));
+    for (int i = 0; i < 8; i++)
+        for (int m = 0; m < 10; m++)
+            out[m * 8 + i] = static_cast<float>(m == 0 ? tbl[i][m] * tbl[i][m] : tbl[i][m]);
+    return PTB200_OK;
+}
+
+int ptb200_read_file(const char *path, size_t *file_size, void *buffer, size_t buffer_size) {
+    if (path == nullptr || buffer == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_read_file: NULL argument");
+    struct stat sb;
+    if (stat(path, &sb) == -1)
+        return fail(PTB200_EIO, "failed to get file %s", path);  // data_utils.h:59-62
+    if (!S_ISREG(sb.st_mode))
+        return fail(PTB200_EIO, "%s is not a file, please enter a file", path);  // :63-66
+    FILE *f = fopen(path, "rb");
+    if (f == nullptr)
+        return fail(PTB200_EIO, "Open file failed. path = %s", path);  // :70-73
+    const size_t size = static_cast<size_t>(sb.st_size);
+    if (size == 0) {
+        fclose(f);
+        return fail(PTB200_EIO, "file size is 0");  // :77-81
+    }
+    if (size > buffer_size) {
+        fclose(f);
+        return fail(PTB200_EIO, "file size is larger than buffer size");  // :82-86
+    }
+    const size_t got = fread(buffer, 1, size, f);
+    fclose(f);
+    if (got != size)
+        return fail(PTB200_EIO, "short read on %s", path);
+    if (file_size != nullptr)
+        *file_size = size;
+    return PTB200_OK;
+}
+
+int ptb200_write_file(const char *path, const void *buffer, size_t size) {
+    if (buffer == nullptr)
+        return fail(PTB200_EINVAL, "Write file failed. buffer is nullptr");  // data_utils.h:103-106
+    if (path == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_write_file: NULL path");
+    const int fd = open(path, O_RDWR | O_CREAT | O_TRUNC, S_IRUSR | S_IWRITE);  // :108
+    if (fd < 0)
+        return fail(PTB200_EIO, "Open file failed. path = %s", path);
+    size_t done = 0;
+    const char *src = static_cast<const char *>(buffer);
+    while (done < size) {  // the reference issues one write(); large buffers need the loop
+        const ssize_t w = write(fd, src + done, size - done);
+        if (w < 0) {
+            if (errno == EINTR)
+                continue;
+            break;
+        }
+        done += static_cast<size_t>(w);
+    }
+    close(fd);
+    if (done != size)
+        return fail(PTB200_EIO, "Write file Failed.");  // :116-119
+    return PTB200_OK;
+}
+
+int ptb200_write_ppm(const char *path, int32_t width, int32_t height, const uint8_t *image) {
+    if (path == nullptr || image == nullptr || width < 1 || height < 1)
+        return fail(PTB200_EINVAL, "ptb200_write_ppm: bad argument");
+    // Build the whole text in memory: "R G B " per pixel, one line per row (data_visualization.py:11-17).
+    std::string out;
+    out.reserve(static_cast<size_t>(width) * height * 12 + 32);
+    char head[64];
+    snprintf(head, sizeof head, "P3\n%d %d\n255\n", width, height);
+    out += head;
+    char num[16];
+    for (int r = 0; r < height; r++) {
+        for (int x = 0; x < width; x++) {
+            const uint8_t *px = image + (static_cast<size_t>(r) * width + x) * 3;
+            const int len = snprintf(num, sizeof num, "%d %d %d ", px[0], px[1], px[2]);
+            out.append(num, static_cast<size_t>(len));
+        }
+        out += '\n';
+    }
+    FILE *f = fopen(path, "w");
+    if (f == nullptr)
+        return fail(PTB200_EIO, "Open file failed. path = %s", path);
+    const size_t w = fwrite(out.data(), 1, out.size(), f);
+    const int rc = fclose(f);
+    if (w != out.size() || rc != 0)
+        return fail(PTB200_EIO, "Write file Failed.");
+    return PTB200_OK;
+}
+
+int ptb200_measure_fp32(int32_t kind, int32_t iters, double *gops_out, double *ms_out) {
+    if (gops_out == nullptr || ms_out == nullptr || iters < 1 || kind < 0 || kind > 7)
+        return fail(PTB200_EINVAL, "ptb200_measure_fp32: bad argument");
+    int rc = check_device("ptb200_measure_fp32");
+    if (rc != PTB200_OK)
+        return rc;
+    cudaError_t e = measure_fp32(kind, iters, gops_out, ms_out);
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_measure_fp32");
+}
+
+}  // extern "C"

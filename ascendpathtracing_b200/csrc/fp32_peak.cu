@@ -1,0 +1,113 @@
+// Measurement support: register-only, dependent-free micro-kernels that establish what the FP32 issue
+// path of this GPU sustains ("measure it on the box with a dependent-free FFMA micro-kernel").
+// The radiance kernel is bound by FP32 instruction issue (FADD/FMUL singly rounded, never FFMA), so its
+// roofline denominator is measured here rather than assumed.
+#include "pt_host.h"
+
+namespace ptb200 {
+namespace {
+
+constexpr int kChains = 8;
+constexpr int kUnroll = 8;
+
+template <int KIND> __global__ void __launch_bounds__(256) peak_kernel(int iters, float x, float y, float *out) {
+    float a[kChains];
+    float2 a2[kChains];
+#pragma unroll
+    for (int j = 0; j < kChains; j++) {
+        a[j] = 1.0f + 0.001f * (threadIdx.x + j);
+        a2[j] = make_float2(a[j], a[j] + 0.5f);
+    }
+    const float2 x2 = make_float2(x, x), y2 = make_float2(y, y);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+#pragma unroll
+            for (int j = 0; j < kChains; j++) {
+                if (KIND == 0) {
+                    a[j] = __fmaf_rn(a[j], x, y);
+                } else if (KIND == 1) {
+                    a[j] = __fmul_rn(a[j], x);
+                    a[j] = __fadd_rn(a[j], y);
+                } else if (KIND == 2) {
+                    a2[j] = __ffma2_rn(a2[j], x2, y2);
+                } else if (KIND == 3) {
+                    a2[j] = __fmul2_rn(a2[j], x2);
+                    a2[j] = __fadd2_rn(a2[j], y2);
+                } else if (KIND == 4) {
+                    a[j] = __fadd_rn(a[j], y);
+                    a[j] = (a[j] > 3.0f) ? x : a[j];
+                } else if (KIND == 5) {
+                    a[j] = __frsqrt_rn(a[j]);
+                } else if (KIND == 6) {
+                    a[j] = __fsqrt_rn(__fadd_rn(a[j], y));
+                } else if (KIND == 7) {
+                    a[j] = __fdiv_rn(x, __fadd_rn(a[j], y));
+                }
+            }
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kChains; j++)
+        s += a[j] + a2[j].x + a2[j].y;
+    if (s == 123.456f)
+        out[0] = s;  // never true in practice; keeps the chains alive
+}
+
+template <int KIND> cudaError_t run(int iters, int grid, cudaStream_t st) {
+    peak_kernel<KIND><<<grid, 256, 0, st>>>(iters, 1.0000001f, 1e-7f, nullptr);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms_out) {
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess)
+        return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+        return e;
+    const int grid = sms * 8;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    auto launch = [&](int it) -> cudaError_t {
+        switch (kind) {
+        case 0: return run<0>(it, grid, nullptr);
+        case 1: return run<1>(it, grid, nullptr);
+        case 2: return run<2>(it, grid, nullptr);
+        case 3: return run<3>(it, grid, nullptr);
+        case 4: return run<4>(it, grid, nullptr);
+        case 5: return run<5>(it, grid, nullptr);
+        case 6: return run<6>(it, grid, nullptr);
+        case 7: return run<7>(it, grid, nullptr);
+        default: return cudaErrorInvalidValue;
+        }
+    };
+    if ((e = launch(iters / 4 + 1)) != cudaSuccess)  // warm-up
+        return e;
+    cudaEventRecord(t0, nullptr);
+    if ((e = launch(iters)) != cudaSuccess)
+        return e;
+    cudaEventRecord(t1, nullptr);
+    if ((e = cudaEventSynchronize(t1)) != cudaSuccess)
+        return e;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    // lane-operations per chain step: packed kinds do 2 lanes' worth; alternating kinds issue 2 instructions
+    double per_step = 1.0;
+    if (kind == 1 || kind == 4) per_step = 2.0;
+    if (kind == 2) per_step = 2.0;
+    if (kind == 3) per_step = 4.0;
+    if (kind == 6 || kind == 7) per_step = 1.0;  // counts sqrt / div results (the feeding FADD is not counted)
+    const double ops = static_cast<double>(grid) * 256.0 * iters * kUnroll * kChains * per_step;
+    *gops = ops / (ms * 1e-3) / 1e9;
+    *ms_out = ms;
+    return cudaSuccess;
+}
+
+}  // namespace ptb200

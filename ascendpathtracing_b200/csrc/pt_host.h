@@ -1,0 +1,36 @@
+// Internal host-side declarations shared by the .cu files of libptb200.so.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <mutex>
+
+#include "../../include/ptb200.h"
+
+namespace ptb200 {
+
+constexpr int kTraceThreads = 256;
+
+// trace_kernels.cu -- paths [first, first+count) of N-path SoA buffers; stats (nullable, device) gets
+// the number of ray segments actually traced added to it.
+cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *rays, const float *spheres, float *colors, int64_t n,
+                        int64_t first, int64_t count, unsigned long long *stats);
+
+// raygen_kernels.cu -- camera rays of the path range [path0, path0+m) of a W x H x S image into an
+// SoA [6][m] buffer.  uniforms (nullable): 2 doubles per ray, uniforms[0] belongs to path0.
+cudaError_t gen_rays(cudaStream_t stream, const PtParams &p, const double *uniforms, uint64_t seed, int64_t path0, int64_t m,
+                     float *rays);
+
+// resolve_kernels.cu -- pixels [pix0, pix0+npix) in x-major order (pixel = x*H + y) from colours SoA
+// [3][cn] whose element 0 is the first sample of pixel `pix0`; image points at the full
+// [H][img_w][3] output whose column 0 is image column x_origin.
+cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *colors, int64_t cn, int64_t pix0, int64_t npix,
+                           uint8_t *image, int32_t x_origin, int32_t img_w);
+
+// fp32_peak.cu
+cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms);
+
+// error plumbing (capi.cu)
+int fail(int code, const char *fmt, ...);
+int fail_cuda(cudaError_t e, const char *what);
+
+}  // namespace ptb200

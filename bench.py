@@ -1,0 +1,293 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: Mpaths/s of the radiance hot path on BASELINE.json config C2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "c2"): the reference's 8-sphere Cornell scene, 1024 x 768, SAMPLES = 16 (64 spp),
+depth 5  ->  50 331 648 paths per GPU, 24 B of rays in and 12 B of colour out per path.  One step = one pass of
+the hot path over that batch: render_do_ex (trace) + resolve to the 8-bit frame (+ for N > 1 the NCCL gather of
+the per-GPU 8-bit stripes, the only exchange the path has).  Rays are generated on the device (counter-based
+RNG) before the timed region and stay resident in HBM; the 1.2 GB ray buffer is ~10x the 126 MB L2, so
+every step streams its input from HBM (config.l2 = "inputs larger than L2").
+
+Printed JSON (one line, rank 0): value = paths of all ranks / max-over-ranks device time; roofline = FP32 issue
+roofline of the trace kernel (algorithmic FLOPs = N*(depth*(19*8+33)+3)) against the FFMA peak
+measured live on this GPU by the library's dependent-free micro-kernel; e2e = the same metric through
+ptb200_render_host with pinned HOST buffers (H2D of rays and D2H of colours inside the timed region);
+cpu_baseline = the reference's own kernel (oracle/_ref, compiled from the reference sources) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, S, DEPTH, NSPH = 1024, 768, 16, 5, 8
+FLOPS_PER_PATH = DEPTH * (19 * NSPH + 33) + 3  # 928, SURVEY.md 8a/8d
+BYTES_PER_PATH = 36
+CPU_SAMPLE = (1024, 1024, 1, 5)                # 4 194 304 paths of the same scene/camera/depth
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_run(threads):
+    """One pass of the reference's own kernel (oracle/_ref) over the bounded sample. Returns (seconds, paths, kind)."""
+    from oracle import oracle as O
+    w, h, s, d = CPU_SAMPLE
+    n = w * h * s * 4
+    rays = O.gen_rays_from_uniforms(w, h, s, 0, w, O.philox_uniforms(1, 0, n))
+    sph = O.gen_spheres()
+    if O.ref_available(w, h, s, d):
+        t = time.perf_counter()
+        O.ref_render(rays, sph, w, h, s, d, threads=threads)
+        return time.perf_counter() - t, n, "reference"
+    O.set_threads(threads)
+    t = time.perf_counter()
+    O.trace(rays, sph, depth=d)
+    return time.perf_counter() - t, n, "port"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    cores = host_threads()
+    threads = min(8, cores)  # the reference runs 8 blocks (src/main.cpp:18): at most 8-way parallel
+    for _ in range(args.warmup):
+        cpu_reference_run(threads)
+    tot_t, tot_n, kind = 0.0, 0, "reference"
+    for _ in range(args.steps):
+        t, n, kind = cpu_reference_run(threads)
+        tot_t += t
+        tot_n += n
+    v = tot_n / tot_t / 1e6
+    w, h, s, d = CPU_SAMPLE
+    line = {"impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c2", "scene": "reference 8-sphere Cornell box", "width": W, "height": H, "spp": 4 * S, "depth": DEPTH,
+                       "paths_per_gpu": W * H * 4 * S},
+            "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": threads, "kind": kind,
+                             "sample": f"{w}x{h}x{4 * s}spp = {w * h * s * 4} paths of the c2 scene/camera per step, reference src/render.cpp "
+                                       f"compiled -O2 against oracle/shim, {threads} of its 8 blocks in parallel"},
+            "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "grays_per_s": v * DEPTH / 1e3}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import ascendpathtracing_b200 as pt
+
+    if not torch.cuda.is_available() or pt.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # The job: a (W*world) x H frame at 64 spp; rank r owns columns [W*r, W*(r+1)) = one c2-sized stripe.
+    p_job = pt.default_params(width=W * world, height=H, samples=S, depth=DEPTH)
+    p = pt.default_params(width=W, height=H, samples=S, depth=DEPTH)  # the stripe as its own N-path problem
+    n = p.n_paths
+    x0, x1 = W * rank, W * (rank + 1)
+    d_rays = torch.empty(6 * n, dtype=torch.float32, device="cuda")
+    pt.gen_rays(p_job, d_rays, x0=x0, x1=x1, seed=2024)
+    d_sph = torch.from_numpy(pt.default_scene()).cuda()
+    d_col = torch.empty(3 * n, dtype=torch.float32, device="cuda")
+    d_img = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
+    d_all = torch.zeros((world, H, W, 3), dtype=torch.uint8, device="cuda") if world > 1 else None
+    torch.cuda.synchronize()
+
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def step(i=None):
+        if i is not None:
+            k_ev[i][0].record()
+        pt.render_do_ex(p, d_rays, d_sph, d_col)   # launches: pack_scene + trace
+        if i is not None:
+            k_ev[i][1].record()
+        pt.resolve(p, d_col, d_img)                 # launch: resolve
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_img)  # final assembly of the 8-bit stripes over NVLink
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        step(i)
+    t1.record()
+    fence()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t0.elapsed_time(t1)
+    trace_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    if world > 1:
+        t = torch.tensor([ms, trace_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, trace_ms = float(t[0]), float(t[1])
+    ms_per_step = ms / args.steps
+    value = n * world / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI entry (every rank, its own stripe) ----
+    e2e = None
+    if not args.no_e2e:
+        h_rays = torch.empty(6 * n, dtype=torch.float32).pin_memory()
+        h_rays.copy_(d_rays)
+        h_col = torch.empty(3 * n, dtype=torch.float32).pin_memory()
+        h_sph = pt.default_scene()
+        e_steps = max(2, min(args.steps, 5))
+        pt.render_host(p, h_rays, h_sph, h_col)  # warm-up (workspace arena allocation)
+        fence()
+        te = time.perf_counter()
+        for _ in range(e_steps):
+            pt.render_host(p, h_rays, h_sph, h_col)  # synchronous: returns when the colours are in host memory
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - te) * 1e3 / e_steps
+        if world > 1:
+            t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t[0])
+        assert torch.equal(h_col.view(torch.int32), d_col.cpu().view(torch.int32)), "e2e result differs from the device-resident result"
+        e2e = {"value": n * world / (e_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": 24 * n + 512, "d2h_bytes_per_step": 12 * n,
+               "ms_per_step": e_ms, "steps": e_steps, "api": "ptb200_render_host (pinned host rays in, host colours out, 3-stream chunked overlap)"}
+        del h_rays, h_col
+
+    if rank == 0:
+        pk = peaks()
+        ffma_gops, _ = pt.measure_fp32(0, 4000)
+        fadd_gops, _ = pt.measure_fp32(1, 4000)
+        peak_tflops = 2.0 * ffma_gops / 1e3
+        achieved = FLOPS_PER_PATH * n / (trace_ms * 1e-3) / 1e12
+        hbm_peak = pk.get("hbm_gbs")
+        roofline = {"bound": "fp32", "kernel": "trace_paths_kernel<8,true>", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tflops, "traffic": None,
+                    "peak_source": "measured live: dependent-free FFMA micro-kernel (ptb200_measure_fp32 kind 0), 2 FLOP per FFMA",
+                    "kernel_ms": trace_ms, "algorithmic_flops_per_path": FLOPS_PER_PATH,
+                    "exact_mode_ceiling": "every op is a singly rounded FADD/FMUL (no FFMA): at most 0.5 of the FFMA-FLOP peak",
+                    "fadd_fmul_issue_peak_gops": fadd_gops, "ffma_issue_peak_gops": ffma_gops,
+                    "hbm": {"achieved_gbs": BYTES_PER_PATH * n / (trace_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                            "frac": (BYTES_PER_PATH * n / (trace_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None}}
+        line = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "c2", "scene": "reference 8-sphere Cornell box", "width": W, "height": H, "spp": 4 * S, "depth": DEPTH,
+                           "paths_per_gpu": n, "l2": "inputs larger than L2 (1.2 GB of rays per step vs 126 MB)",
+                           "step": "render_do_ex + resolve" + (" + NCCL all_gather of 8-bit stripes" if world > 1 else ""),
+                           "rng": "counter-based (Philox4x32-10), rays resident in HBM"},
+                "grays_per_s": value * DEPTH / 1e3, "grays_note": "reference-equivalent segments (N*depth); early termination traces ~78% of them",
+                "roofline": roofline, "clocks": clocks, "gpu_launches": 3 * args.steps,
+                "e2e": e2e}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_threads()
+            threads = min(8, cores)
+            t, cn, kind = cpu_reference_run(threads)
+            w_, h_, s_, _ = CPU_SAMPLE
+            line["cpu_baseline"] = {"value": cn / t / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": kind, "host_cores": cores,
+                                    "sample": f"{w_}x{h_}x{4 * s_}spp = {cn} paths of the c2 scene/camera, one pass, {t:.2f} s wall"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+/* ptb200.h -- C ABI of libptb200.so, the B200 (sm_100a) drop-in for the per-pixel radiance operator of
+ * KVM-Explorer/AscendPathTracing.  Citations are file:line into the reference repository.
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Unless a function says "host", every buffer
+ * pointer is a DEVICE pointer owned by the caller, and every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = the legacy default stream) exactly like the reference's
+ * render_do (src/render.cpp:264-266; the caller synchronises, src/main.cpp:75).
+ *
+ * Return values: 0 on success, otherwise a negative PTB200_E* code or a positive cudaError_t.
+ * ptb200_last_error() returns a thread-local human-readable message for the last failure.
+ * There is no CPU fallback anywhere: without a CUDA device every compute entry fails with
+ * PTB200_ENODEV (or the CUDA error).
+ *
+ * Buffer layouts (identical to the reference's files):
+ *   rays     float32 SoA [6][N]   ox,oy,oz,dx,dy,dz planes           (scripts/gen_data.py:65-71)
+ *   spheres  float32 SoA [10][stride] r^2,x,y,z,ex,ey,ez,cr,cg,cb    (scripts/gen_data.py:106-127,
+ *            src/rt_helper.h:91-103); the reference is stride = 8 padded to 512 bytes
+ *   colors   float32 SoA [3][N]   R,G,B planes                        (src/render.cpp:218-220)
+ *   image    uint8 [H rows, top first][W][3]                          (scripts/data_visualization.py:11-57)
+ *   N = width * height * 4 * samples, path index ((((x*H + y)*2 + sy)*2 + sx)*S + k)  (gen_data.py:32-36)
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB200_ABI_VERSION 1
+
+/* exported from libptb200.so (the library is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define PTB200_API __attribute__((visibility("default")))
+#else
+#define PTB200_API
+#endif
+
+enum {
+    PTB200_OK = 0,
+    PTB200_EINVAL = -1,  /* bad argument (null pointer, size rule violated, ...) */
+    PTB200_ENODEV = -2,  /* no CUDA device */
+    PTB200_ENOMEM = -3,  /* arena exhausted / allocation failed */
+    PTB200_EIO = -4      /* file I/O failed */
+};
+
+/* Run-time form of the reference's compile-time configuration (src/common.h:4-14) and literals:
+ * depth 5 (src/render.cpp:141), light index 7 (src/rt_helper.h:776), emission 12 (src/render.cpp:194-196). */
+typedef struct PtParams {
+    int32_t width;          /* WIDTH   (common.h:4)  */
+    int32_t height;         /* HEIGHT  (common.h:5)  */
+    int32_t samples;        /* SAMPLES (common.h:6): samples per sub-pixel; spp = 4*samples */
+    int32_t depth;          /* bounces per path (render.cpp:141), reference = 5 */
+    int32_t sphere_count;   /* SPHERE_NUM (common.h:10), reference = 8 */
+    int32_t sphere_stride;  /* floats between members in the sphere SoA; reference = 8 */
+    int32_t light_index;    /* sphere that ends a path (rt_helper.h:776), reference = 7 */
+    float emission_scale;   /* final multiplier (render.cpp:194-196), reference = 12 */
+    int32_t flags;          /* PTB200_F_* */
+    int32_t reserved;
+} PtParams;
+
+enum {
+    /* Stop tracing a path once its colour can no longer change (light hit, or throughput exactly 0).
+     * Bit-identical results to the reference's fixed-depth loop. Default on;
+     * set PTB200_F_FIXED_DEPTH to trace every bounce like the reference does. */
+    PTB200_F_FIXED_DEPTH = 1
+};
+
+/* Fills *p with the reference defaults (16x16, SAMPLES=1, depth 5, 8 spheres, light 7, x12). */
+PTB200_API void ptb200_default_params(PtParams *p);
+
+PTB200_API int ptb200_abi_version(void);
+PTB200_API const char *ptb200_last_error(void);
+/* Number of CUDA devices visible (0 when none / no driver). Never fails. */
+PTB200_API int ptb200_device_count(void);
+
+/* ---- the reference's kernel entry points ------------------------------------------------------ */
+
+/* Replaces `extern "C" __global__ __aicore__ void render(GM_ADDR rays, GM_ADDR spheres, GM_ADDR colors)`
+ * (src/render.cpp:253-259, declared src/main.cpp:13).  Same three opaque byte pointers in the same
+ * order.  Sizes come from the library's legacy configuration (ptb200_set_legacy_config; initially the
+ * reference's common.h values).  Launches on the default stream and returns after completion, like
+ * ICPU_RUN_KF (src/main.cpp:37).  Errors are logged to stderr in the style of CHECK_ACL
+ * (src/data_utils.h:41-47) because the signature returns void. */
+PTB200_API void render(uint8_t *rays, uint8_t *spheres, uint8_t *colors);
+
+/* Replaces `void render_do(uint32_t blockDim, void *l2ctrl, void *stream, uint8_t *rays, uint8_t *spheres,
+ * uint8_t *colors)` (src/render.cpp:264-266, declared src/main.cpp:9-10).  Asynchronous on `stream`.
+ * blockDim and l2ctrl are accepted and ignored (the reference passes 8 and nullptr, src/main.cpp:18,74). */
+PTB200_API void render_do(uint32_t blockDim, void *l2ctrl, void *stream, uint8_t *rays, uint8_t *spheres, uint8_t *colors);
+
+/* The reference fixes W/H/SAMPLES at compile time (src/common.h:4-6, src/render.cpp:256); the two legacy
+ * entry points above use this process-wide configuration instead. Validates the reference's preconditions
+ * (src/render.cpp:68-73: N % 8 == 0 and (N/8) % 128 == 0). */
+PTB200_API int ptb200_set_legacy_config(const PtParams *p);
+PTB200_API void ptb200_get_legacy_config(PtParams *p);
+
+/* Run-time-parameter sibling of render_do.  Traces paths [first, first+count) of the N-path buffers
+ * (count < 0 means "to the end"); the reference's per-core slice (src/render.cpp:24-27) is first =
+ * b*N/8, count = N/8.  Any N >= 0 is accepted (no divisibility rule). */
+PTB200_API int render_do_ex(const PtParams *p, void *stream, const uint8_t *rays, const uint8_t *spheres, uint8_t *colors,
+                 int64_t first, int64_t count);
+
+/* ---- the steps either side of the kernel ---------------------------------------- */
+
+/* Camera rays of image columns [x0, x1) (scripts/gen_data.py:21-75) written as float32 SoA [6][M],
+ * M = (x1-x0)*H*4*S, in the reference's order.  `uniforms` (device, 2 doubles per ray) replays a
+ * recorded random stream -- the reference's is NumPy MT19937 seed 0, see ptb200_mt19937_uniforms --
+ * and may be NULL, in which case the counter-based generator (Philox4x32-10 keyed by `seed`, counter =
+ * global path index) supplies them. */
+PTB200_API int ptb200_gen_rays(const PtParams *p, void *stream, const double *uniforms, uint64_t seed, int32_t x0, int32_t x1,
+                    float *rays);
+
+/* HOST helper: the doubles np.random.seed(seed); np.random.rand() yields (gen_data.py:37-39,438),
+ * skipping the first `skip` doubles; ray i consumes doubles 2i and 2i+1.  Writes n doubles to host memory. */
+PTB200_API int ptb200_mt19937_uniforms(uint32_t seed, uint64_t skip, uint64_t n, double *out_host);
+
+/* HOST helper: the 512-byte scene of scripts/gen_data.py:92-132 (128 floats) into host memory. */
+PTB200_API int ptb200_default_scene(float *out128_host);
+
+/* Resolve (scripts/data_visualization.py:20-59): colors float32 SoA [3][N] -> uint8 image of columns
+ * [x0, x1): out is [H][x1-x0][3].  Bit-exact with NumPy's float32 pairwise mean. */
+PTB200_API int ptb200_resolve(const PtParams *p, void *stream, const float *colors, int32_t x0, int32_t x1, uint8_t *image);
+
+/* Fused production path: generate, trace and resolve columns [x0, x1) without materialising rays or
+ * per-path colours.  uniforms as in ptb200_gen_rays (NULL -> counter-based RNG). image: [H][x1-x0][3].
+ * `stats` (device, may be NULL) receives 2 uint64: paths traced, ray segments actually traced. */
+PTB200_API int ptb200_render_image(const PtParams *p, void *stream, const uint8_t *spheres, const double *uniforms, uint64_t seed,
+                        int32_t x0, int32_t x1, uint8_t *image, uint64_t *stats);
+
+/* ---- whole-job host-buffer entry (what the reference's main() does, src/main.cpp:46-92) --------- */
+
+/* HOST buffers in, HOST buffer out: arena allocation, H2D of rays+spheres, render, D2H of colours,
+ * synchronous.  This is the end-to-end call bench.py times. */
+PTB200_API int ptb200_render_host(const PtParams *p, const float *rays_host, const float *spheres_host, float *colors_host);
+
+/* ---- device arena: replaces src/allocator.h's MemoryPool for the big buffers -------------------- */
+
+typedef struct PtArena PtArena;
+/* One cudaMalloc of `bytes`; first-fit free list with split on alloc and coalescing on free, the
+ * semantics of Allocator::Init/Alloc/Free (src/allocator.h:54-151), 256-byte granularity. */
+PTB200_API int ptb200_arena_create(size_t bytes, PtArena **out);
+/* Same bookkeeping over memory the caller already owns (e.g. a framework tensor): [base, base+bytes) is
+ * never dereferenced by the arena itself and is not freed by ptb200_arena_destroy. */
+PTB200_API int ptb200_arena_wrap(void *base, size_t bytes, PtArena **out);
+PTB200_API int ptb200_arena_destroy(PtArena *a);
+/* Returns a device pointer or NULL when no free block is large enough (allocator.h:103-105 throws). */
+PTB200_API void *ptb200_arena_alloc(PtArena *a, size_t bytes);
+/* PTB200_EINVAL for a pointer the arena does not own or a double free (allocator.h:262-270 warns). */
+PTB200_API int ptb200_arena_free(PtArena *a, void *ptr);
+PTB200_API size_t ptb200_arena_capacity(const PtArena *a);
+PTB200_API size_t ptb200_arena_in_use(const PtArena *a);
+PTB200_API size_t ptb200_arena_largest_free(const PtArena *a);
+
+/* ---- file I/O with the reference's semantics (src/data_utils.h:55-122), C linkage ---------------- */
+
+/* Reads the whole file into buffer (fails if missing, empty or larger than buffer_size). */
+PTB200_API int ptb200_read_file(const char *path, size_t *file_size, void *buffer_host, size_t buffer_size);
+/* O_RDWR|O_CREAT|O_TRUNC, mode 0600 (data_utils.h:108). */
+PTB200_API int ptb200_write_file(const char *path, const void *buffer_host, size_t size);
+/* ASCII P3 writer (scripts/data_visualization.py:11-17); image is host uint8 [H][W][3]. */
+PTB200_API int ptb200_write_ppm(const char *path, int32_t width, int32_t height, const uint8_t *image_host);
+
+/* ---- measurement support ----------------------------------------------------------------------- */
+
+/* Measures FP32 issue throughput on the current device with dependent-free register-only kernels.
+ * kind: 0 FFMA, 1 FADD/FMUL alternating, 2 FFMA2 (packed f32x2), 3 FADD2/FMUL2 alternating,
+ *       4 FADD + FSETP/FSEL mix, 5 MUFU.RSQ, 6 IEEE sqrt (__fsqrt_rn), 7 IEEE div (__fdiv_rn).
+ * Writes giga-operations per second (one packed op counts as 2 lane-ops; FFMA counts as 1 op here --
+ * multiply by 2 for FLOP) and the kernel milliseconds. */
+PTB200_API int ptb200_measure_fp32(int32_t kind, int32_t iters, double *gops_out, double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

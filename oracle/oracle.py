@@ -33,6 +33,10 @@ def lib():
         L.pto_mt_words.argtypes = [ctypes.c_uint32, _u32p, ctypes.c_int64]
         L.pto_mt_doubles.restype = None
         L.pto_mt_doubles.argtypes = [ctypes.c_uint32, ctypes.c_int64, _f64p, ctypes.c_int64]
+        L.pto_philox4x32_10.restype = None
+        L.pto_philox4x32_10.argtypes = [_u32p, _u32p, _u32p]
+        L.pto_philox_uniforms.restype = None
+        L.pto_philox_uniforms.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64, _f64p]
         L.pto_camera.restype = None
         L.pto_camera.argtypes = [ctypes.c_int, ctypes.c_int, _f64p]
         L.pto_gen_rays_from_uniforms.restype = None
@@ -86,6 +90,18 @@ def mt_words(seed, n):
 def mt_doubles(seed, n, skip=0):
     out = np.zeros(n, dtype=np.float64)
     lib().pto_mt_doubles(seed, skip, out, n)
+    return out
+
+
+def philox4x32_10(ctr, key):
+    out = np.zeros(4, dtype=np.uint32)
+    lib().pto_philox4x32_10(np.asarray(ctr, dtype=np.uint32), np.asarray(key, dtype=np.uint32), out)
+    return out
+
+
+def philox_uniforms(seed, first, n):
+    out = np.zeros(2 * n, dtype=np.float64)
+    lib().pto_philox_uniforms(seed, first, n, out)
     return out
 
 

@@ -230,6 +230,35 @@ void pto_mt_doubles(uint32_t seed, int64_t skip, double *out, int64_t n) {
         out[i] = pto_mt_double(&st);
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Counter-based generator of the production path: Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).
+ * NOT part of the reference ("parity unpinned" by it): pinned instead by the Random123 known-answer
+ * vectors in tests/test_oracle.py.  Uniforms are formed from word pairs exactly like genrand_res53.
+ * ---------------------------------------------------------------------------------------------- */
+void pto_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* uniforms for global path indices [first, first+n): out[2i], out[2i+1] */
+void pto_philox_uniforms(uint64_t seed, uint64_t first, int64_t n, double *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t g = first + (uint64_t)i;
+        uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), 0, 0}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, w[4];
+        pto_philox4x32_10(ctr, key, w);
+        out[2 * i] = ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) / 9007199254740992.0;
+        out[2 * i + 1] = ((double)(w[2] >> 5) * 67108864.0 + (double)(w[3] >> 6)) / 9007199254740992.0;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Camera (gen_data.py:24-29), all binary64.  cam[0..2] = position, [3..5] = direction, [6..8] = cx,
  * [9..11] = cy.  np.linalg.norm(v) = sqrt(v.dot(v)); the 3-term dot is accumulated left to right.
