@@ -43,6 +43,24 @@ template <int KIND> __global__ void __launch_bounds__(256) peak_kernel(int iters
                     a[j] = __fsqrt_rn(__fadd_rn(a[j], y));
                 } else if (KIND == 7) {
                     a[j] = __fdiv_rn(x, __fadd_rn(a[j], y));
+                } else if (KIND == 8) {  // FMUL2 alone (nothing to contract with)
+                    a2[j] = __fmul2_rn(a2[j], x2);
+                } else if (KIND == 9) {  // FADD2 alone
+                    a2[j] = __fadd2_rn(a2[j], y2);
+                } else if (KIND == 10) {  // the exact "mixed" pattern: packed product, scalar sums of its halves
+                    const float2 p = __fmul2_rn(a2[j], x2);
+                    a2[j] = make_float2(__fadd_rn(p.x, y), __fadd_rn(p.y, y));
+                } else if (KIND == 11) {  // FADD2 + two ALU-pipe selects: does the ALU work hide behind the packed op?
+                    a2[j] = __fadd2_rn(a2[j], y2);
+                    a2[j].x = (a2[j].x > 3.0f) ? x : a2[j].x;
+                    a2[j].y = (a2[j].y > 3.0f) ? x : a2[j].y;
+                } else if (KIND == 12) {  // pure MUFU.RSQ
+                    float r;
+                    asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a[j]));
+                    a[j] = r;
+                } else if (KIND == 13) {  // FMNMX (ALU pipe) alone
+                    a[j] = fminf(a[j], x) ;
+                    a[j] = fmaxf(a[j], y) ;
                 }
             }
         }
@@ -83,6 +101,12 @@ cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms_out) {
         case 5: return run<5>(it, grid, nullptr);
         case 6: return run<6>(it, grid, nullptr);
         case 7: return run<7>(it, grid, nullptr);
+        case 8: return run<8>(it, grid, nullptr);
+        case 9: return run<9>(it, grid, nullptr);
+        case 10: return run<10>(it, grid, nullptr);
+        case 11: return run<11>(it, grid, nullptr);
+        case 12: return run<12>(it, grid, nullptr);
+        case 13: return run<13>(it, grid, nullptr);
         default: return cudaErrorInvalidValue;
         }
     };
@@ -104,6 +128,10 @@ cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms_out) {
     if (kind == 2) per_step = 2.0;
     if (kind == 3) per_step = 4.0;
     if (kind == 6 || kind == 7) per_step = 1.0;  // counts sqrt / div results (the feeding FADD is not counted)
+    if (kind == 8 || kind == 9) per_step = 2.0;   // one packed instruction = 2 lane-ops
+    if (kind == 10) per_step = 4.0;               // FMUL2 (2) + 2 FADD
+    if (kind == 11) per_step = 2.0;               // counts the FADD2 lanes only; the 4 ALU ops ride along
+    if (kind == 13) per_step = 2.0;
     const double ops = static_cast<double>(grid) * 256.0 * iters * kUnroll * kChains * per_step;
     *gops = ops / (ms * 1e-3) / 1e9;
     *ms_out = ms;

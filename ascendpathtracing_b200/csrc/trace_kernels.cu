@@ -9,6 +9,8 @@
 // divergence: a lane whose path has settled (light reached / throughput zero -- bit-identical early
 // termination) swaps in its next path, already prefetched, while its neighbours carry on.
 // The scene lives in the constant bank (immediate operands) plus a shared copy for per-lane lookups.
+#include <cuda_pipeline.h>
+
 #include "pt_device.cuh"
 #include "pt_host.h"
 
@@ -22,15 +24,18 @@ __global__ void pack_scene_kernel(const float *__restrict__ spheres, int nsph, i
     if (threadIdx.x == 0)
         ok = 1;
     __syncthreads();
-    for (int k = threadIdx.x; k < nsph; k += blockDim.x) {
-        dst->r2[k] = spheres[0 * stride + k];
+    const int padded = (nsph + 1) & ~1;  // the pairwise tests read one sphere past an odd count
+    for (int k = threadIdx.x; k < padded; k += blockDim.x) {
+        if (k >= nsph) {  // never-hit sphere: NaN centre -> NaN roots -> both compares false
+            dst->nr2[k] = 0.0f;
+            dst->cx[k] = dst->cy[k] = dst->cz[k] = __int_as_float(0x7fc00000);
+            continue;
+        }
+        dst->nr2[k] = -spheres[0 * stride + k];
         dst->cx[k] = spheres[1 * stride + k];
         dst->cy[k] = spheres[2 * stride + k];
         dst->cz[k] = spheres[3 * stride + k];
         const float r = spheres[7 * stride + k], g = spheres[8 * stride + k], b = spheres[9 * stride + k];
-        dst->kr[k] = r;
-        dst->kg[k] = g;
-        dst->kb[k] = b;
         // zero-throughput early stop is exact only for finite colours with a clear sign bit
         const unsigned ur = __float_as_uint(r), ug = __float_as_uint(g), ub = __float_as_uint(b);
         if ((ur | ug | ub) >> 31 || !isfinite(r) || !isfinite(g) || !isfinite(b))
@@ -42,66 +47,113 @@ __global__ void pack_scene_kernel(const float *__restrict__ spheres, int nsph, i
 }
 
 // ---- the trace kernel -----------------------------------------------------------------------------
-__device__ __forceinline__ void load_ray(const float *__restrict__ rays, int64_t n, int64_t i, float (&r)[6]) {
-#pragma unroll
-    for (int c = 0; c < 6; c++)
-        r[c] = __ldg(rays + c * n + i);
-}
+// Plane base pointers (already offset to the first path of the launch) travel as kernel parameters: the
+// constant bank feeds IMAD.WIDE directly, so a lane forms an address with one instruction from its 32-bit
+// path index instead of a 64-bit add chain.
+struct TracePlanes {
+    const float *ray[6];
+    float *col[3];
+};
+
+constexpr int kRingBatches = 4;                  // batches of 32 rays in the ring per warp (power of two)
+constexpr int kRing = 32 * kRingBatches;         // ring entries per warp
+constexpr int kWarpsPerBlock = kTraceThreads / 32;
 
 template <int NS, bool EARLY>
-__global__ void __launch_bounds__(kTraceThreads) trace_paths_kernel(const float *__restrict__ rays, float *__restrict__ colors, int64_t n,
-                                                                    int64_t first, int64_t count, int depth, int nsph, int light,
-                                                                    float scale, unsigned long long *__restrict__ stats) {
+__global__ void __launch_bounds__(kTraceThreads) trace_paths_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
+                                                                    int depth, int nsph, int stride, int light, float scale, float one,
+                                                                    unsigned long long *__restrict__ stats) {
     extern __shared__ float4 smem[];
     SceneShared sh;
-    stage_scene_shared(smem, nsph, sh);
+    stage_scene_shared(smem, spheres, nsph, stride, sh);
     const bool zero_stop = c_scene_zero_stop_ok != 0;
 
-    const int64_t lanes = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    const int64_t end = first + count;
-    int64_t i = first + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    bool active = i < end;
+    // Persistent warps with path regeneration.  Each warp owns a contiguous range of paths and hands them
+    // out in order: lanes whose path finished in this iteration are ranked by a ballot and take the next
+    // consecutive indices, so the rays they fetch and (to within the few paths in flight) the colours they
+    // store share cache lines even though the lanes are at different bounces of different paths.
+    // The range is streamed through a per-warp shared-memory ring, four coalesced cp.async batches of 32
+    // rays ahead of consumption, so a swap costs six LDS instead of an exposed HBM round trip.
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int warp_in_block = threadIdx.x >> 5;
+    const unsigned int warp = blockIdx.x * kWarpsPerBlock + warp_in_block;
+    const unsigned int nwarps = gridDim.x * kWarpsPerBlock;
+    const unsigned int per = ((count + nwarps - 1) / nwarps + 31u) & ~31u;
+    const unsigned long long wb = static_cast<unsigned long long>(warp) * per;
+    const unsigned int wbeg = wb < count ? static_cast<unsigned int>(wb) : count;
+    const unsigned int wcount = (count - wbeg) < per ? (count - wbeg) : per;  // paths of this warp
+    float *ring = reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * (6 * kRing);
+
+    auto issue_batch = [&](unsigned int b) {  // warp-uniform: every lane commits a (possibly empty) group
+        const unsigned int e = b * 32u + lane;
+        if (e < wcount) {
+            const unsigned int s = e & (kRing - 1);
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+                __pipeline_memcpy_async(ring + c * kRing + s, pl.ray[c] + wbeg + e, sizeof(float));
+        }
+        __pipeline_commit();
+    };
+    unsigned int issued = 0;
+    for (; issued < kRingBatches; issued++)
+        issue_batch(issued);
 
     PathState p;
-    float cur[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
-    if (active)
-        load_ray(rays, n, i, cur);
-    p.ox = cur[0], p.oy = cur[1], p.oz = cur[2], p.dx = cur[3], p.dy = cur[4], p.dz = cur[5];
+    p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
+    p.dz = 1.0f;
     p.rr = p.rg = p.rb = 1.0f;
     p.alive = true;
     int bounce = 0;
-
-    // software prefetch of this lane's next path
-    float nxt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
-    int64_t inext = i + lanes;
-    bool has_next = inext < end;
-    if (has_next)
-        load_ray(rays, n, inext, nxt);
-
     unsigned int segs = 0;
-    while (__any_sync(0xffffffffu, active)) {
+    unsigned int head = 0;      // next unassigned path of the warp's range (warp-uniform)
+    unsigned int mine = 0;      // offset of the path this lane holds
+    bool active = false;        // this lane holds a real path
+    bool want = true;           // this lane needs a (new) path
+
+    for (;;) {
+        const unsigned int wmask = __ballot_sync(0xffffffffu, want);
+        if (wmask != 0u) {  // warp-uniform
+            if (active && want) {  // lanes that finished a path in the previous iteration
+                const unsigned int i = wbeg + mine;
+                pl.col[0][i] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
+                pl.col[1][i] = __fmul_rn(p.rg, scale);
+                pl.col[2][i] = __fmul_rn(p.rb, scale);
+                segs += bounce;
+            }
+            const unsigned int rank = __popc(wmask & ((1u << lane) - 1u));
+            const unsigned int e = head + rank;
+            const bool take = want && e < wcount;
+            __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
+            __syncwarp();              // ... and is visible to the other lanes of the warp
+            if (take) {
+                const unsigned int s = e & (kRing - 1);
+                p.ox = ring[0 * kRing + s], p.oy = ring[1 * kRing + s], p.oz = ring[2 * kRing + s];
+                p.dx = ring[3 * kRing + s], p.dy = ring[4 * kRing + s], p.dz = ring[5 * kRing + s];
+                mine = e;
+            }
+            if (want) {
+                active = take;
+                p.rr = p.rg = p.rb = 1.0f;
+                p.alive = true;
+                bounce = 0;
+                want = false;
+            }
+            head += __popc(wmask);
+            head = head < wcount ? head : wcount;
+            __syncwarp();  // ring reads done before a slot can be refilled
+            if (issued < head / 32u + kRingBatches) {
+                issue_batch(issued);
+                issued++;
+            }
+            if (!__any_sync(0xffffffffu, active))
+                break;
+        }
         float tmin;
         int idx;
-        nearest_hit<NS>(p, nsph, tmin, idx);
-        bounce_and_shade(p, tmin, idx, light, sh);
+        nearest_hit<NS>(p, nsph, one, tmin, idx);
+        bounce_and_shade<EARLY>(p, tmin, idx, light, sh);
         bounce++;
-        segs += active ? 1u : 0u;
-        const bool fin = (bounce >= depth) || (EARLY && path_settled(p, zero_stop));
-        if (active && fin) {
-            colors[i] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
-            colors[n + i] = __fmul_rn(p.rg, scale);
-            colors[2 * n + i] = __fmul_rn(p.rb, scale);
-            i = inext;
-            active = has_next;
-            p.ox = nxt[0], p.oy = nxt[1], p.oz = nxt[2], p.dx = nxt[3], p.dy = nxt[4], p.dz = nxt[5];
-            p.rr = p.rg = p.rb = 1.0f;
-            p.alive = true;
-            bounce = 0;
-            inext = i + lanes;
-            has_next = inext < end;
-            if (has_next)
-                load_ray(rays, n, inext, nxt);
-        }
+        want = active && ((bounce >= depth) || (EARLY && path_settled(p, zero_stop)));
     }
     if (stats != nullptr) {
         unsigned int w = segs;
@@ -159,9 +211,9 @@ cudaError_t ensure_device_state(DeviceState **out) {
 }
 
 template <int NS, bool EARLY>
-cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays, float *colors, int64_t n, int64_t first, int64_t count,
-                         const PtParams &p, unsigned long long *stats) {
-    const size_t smem = sizeof(float4) * 2 * static_cast<size_t>(p.sphere_count);
+cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays, const float *spheres, float *colors, int64_t n,
+                         int64_t first, int64_t count, const PtParams &p, unsigned long long *stats) {
+    const size_t smem = sizeof(float4) * 2 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
     int &occ = s.blocks_per_sm[(NS > 0 ? 2 : 0) + (EARLY ? 1 : 0)];
     if (occ == 0 || NS == 0) {
         cudaError_t e = occupancy<NS, EARLY>(&occ, smem);
@@ -170,12 +222,24 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
         if (occ < 1)
             occ = 1;
     }
-    const int64_t need = (count + kTraceThreads - 1) / kTraceThreads;
     const int64_t cap = static_cast<int64_t>(s.sm_count) * occ;
-    const int grid = static_cast<int>(need < cap ? need : cap);
-    trace_paths_kernel<NS, EARLY><<<grid, kTraceThreads, smem, stream>>>(rays, colors, n, first, count, p.depth, p.sphere_count,
-                                                                         p.light_index, p.emission_scale, stats);
-    return cudaGetLastError();
+    constexpr int64_t kMaxPerLaunch = 1LL << 30;  // 32-bit path indices inside the kernel
+    for (int64_t a = first; a < first + count; a += kMaxPerLaunch) {
+        const int64_t m = (first + count - a < kMaxPerLaunch) ? first + count - a : kMaxPerLaunch;
+        TracePlanes pl;
+        for (int c = 0; c < 6; c++)
+            pl.ray[c] = rays + c * n + a;
+        for (int c = 0; c < 3; c++)
+            pl.col[c] = colors + c * n + a;
+        const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
+        const int grid = static_cast<int>(need < cap ? need : cap);
+        trace_paths_kernel<NS, EARLY><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), p.depth, p.sphere_count,
+                                                                             p.sphere_stride, p.light_index, p.emission_scale, 1.0f, stats);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace
@@ -200,11 +264,11 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
         return e;
     const bool early = !(p.flags & PTB200_F_FIXED_DEPTH);
     if (p.sphere_count == 8)
-        e = early ? launch_trace<8, true>(*s, stream, rays, colors, n, first, count, p, stats)
-                  : launch_trace<8, false>(*s, stream, rays, colors, n, first, count, p, stats);
+        e = early ? launch_trace<8, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats)
+                  : launch_trace<8, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats);
     else
-        e = early ? launch_trace<0, true>(*s, stream, rays, colors, n, first, count, p, stats)
-                  : launch_trace<0, false>(*s, stream, rays, colors, n, first, count, p, stats);
+        e = early ? launch_trace<0, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats)
+                  : launch_trace<0, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats);
     if (e != cudaSuccess)
         return e;
     if ((e = cudaEventRecord(s->scene_free, stream)) != cudaSuccess)
