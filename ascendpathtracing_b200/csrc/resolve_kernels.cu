@@ -13,44 +13,68 @@
 namespace ptb200 {
 namespace {
 
-__device__ __forceinline__ float sum_block_le128(const float *__restrict__ a, int n) {
-    // 8 <= n <= 128
-    float r[8];
+// ---- warp-cooperative form -----------------------------------------------------------------------------
+// One warp resolves kItems (pixel, channel) pairs at a time.  For each pair the 4*S samples are 4 runs of S
+// contiguous floats; eight lanes own one run and play NumPy's eight interleaved accumulators (lane j sums a[j],
+// a[8+j], ... in order), then combine with three xor-shuffles in exactly NumPy's association
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).  Every step of a run reads one full 32-byte sector, and the kItems
+// independent streams keep enough loads in flight to run the colour planes through at HBM speed (a single
+// stream per warp is latency-bound at ~1 TB/s).
+constexpr int kItems = 6;  // 2 pixels x 3 channels
+
+__device__ __forceinline__ void group_block_sum(const float *const (&a)[kItems], int64_t off, int n, int j, float (&r)[kItems]) {
+    // 8 <= n <= 128; lanes j = 0..7 of the group; results valid in lane j == 0
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-        r[j] = a[j];
-    int i = 8;
+    for (int u = 0; u < kItems; u++)
+        r[u] = a[u][off + j];
     const int lim = n - (n % 8);
-    for (; i < lim; i += 8) {
+    for (int i = 8; i < lim; i += 8) {
+        float v[kItems];
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            r[j] = __fadd_rn(r[j], a[i + j]);
+        for (int u = 0; u < kItems; u++)
+            v[u] = a[u][off + i + j];
+#pragma unroll
+        for (int u = 0; u < kItems; u++)
+            r[u] = __fadd_rn(r[u], v[u]);
     }
-    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-    for (; i < n; i++)
-        res = __fadd_rn(res, a[i]);
-    return res;
+#pragma unroll
+    for (int u = 0; u < kItems; u++) {
+        r[u] = __fadd_rn(r[u], __shfl_xor_sync(0xffffffffu, r[u], 1));  // lane0: r0+r1, lane2: r2+r3, ...
+        r[u] = __fadd_rn(r[u], __shfl_xor_sync(0xffffffffu, r[u], 2));  // lane0: (r0+r1)+(r2+r3), lane4: (r4+r5)+(r6+r7)
+        r[u] = __fadd_rn(r[u], __shfl_xor_sync(0xffffffffu, r[u], 4));  // lane0: the NumPy association
+    }
+    for (int i = lim; i < n; i++) {  // sequential tail (only lane 0's value is used)
+#pragma unroll
+        for (int u = 0; u < kItems; u++)
+            r[u] = __fadd_rn(r[u], a[u][off + i]);
+    }
 }
 
-// NumPy pairwise sum without recursion: an explicit stack of pending halves; partial sums are combined in
-// exactly the order the recursive formulation would (post-order).
-__device__ float pairwise_sum(const float *__restrict__ a, int64_t n) {
+// NumPy pairwise sums of kItems runs of equal length n; control flow depends on n only, so the warp agrees.
+__device__ void group_pairwise_sum(const float *const (&a)[kItems], int64_t n, int j, float (&ret)[kItems]) {
     if (n < 8) {
-        float res = 0.0f;
-        for (int64_t i = 0; i < n; i++)
-            res = __fadd_rn(res, a[i]);
-        return res;
+#pragma unroll
+        for (int u = 0; u < kItems; u++) {
+            float res = 0.0f;
+            for (int64_t i = 0; i < n; i++)
+                res = __fadd_rn(res, a[u][i]);
+            ret[u] = res;
+        }
+        return;
     }
-    int64_t off[40], len[40];
-    float left[40];
-    int state[40];  // 0 = fresh, 1 = left half done, 2 = right half done
+    if (n <= 128) {
+        group_block_sum(a, 0, static_cast<int>(n), j, ret);
+        return;
+    }
+    int64_t off[32], len[32];
+    float left[32][kItems];
+    int state[32];
     int sp = 0;
     off[0] = 0, len[0] = n, state[0] = 0;
-    float ret = 0.0f;
     while (sp >= 0) {
         if (state[sp] == 0) {
             if (len[sp] <= 128) {
-                ret = sum_block_le128(a + off[sp], static_cast<int>(len[sp]));
+                group_block_sum(a, off[sp], static_cast<int>(len[sp]), j, ret);
                 sp--;
             } else {
                 int64_t n2 = len[sp] / 2;
@@ -60,48 +84,68 @@ __device__ float pairwise_sum(const float *__restrict__ a, int64_t n) {
                 sp++;
             }
         } else if (state[sp] == 1) {
-            left[sp] = ret;
+#pragma unroll
+            for (int u = 0; u < kItems; u++)
+                left[sp][u] = ret[u];
             int64_t n2 = len[sp] / 2;
             n2 -= n2 % 8;
             state[sp] = 2;
             off[sp + 1] = off[sp] + n2, len[sp + 1] = len[sp] - n2, state[sp + 1] = 0;
             sp++;
         } else {
-            ret = __fadd_rn(left[sp], ret);
+#pragma unroll
+            for (int u = 0; u < kItems; u++)
+                ret[u] = __fadd_rn(left[sp][u], ret[u]);
             sp--;
         }
     }
-    return ret;
 }
 
 __global__ void __launch_bounds__(256) resolve_kernel(const float *__restrict__ colors, int64_t cn, int64_t pix0, int64_t npix, int h, int s,
                                                       uint8_t *__restrict__ image, int x_origin, int img_w) {
-    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= npix * 3)
-        return;
-    const int64_t q = t / 3;  // pixel within the tile
-    const int c = static_cast<int>(t - q * 3);
-    const float *px = colors + c * cn + q * 4 * s;
-    double sum = 0.0;
+    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // warp = 2 consecutive pixels
+    const int64_t q0 = w * 2;
+    if (q0 >= npix)
+        return;  // whole warp
+    const int lane = threadIdx.x & 31;
+    const int k = lane >> 3, j = lane & 7;  // sub-pixel run, accumulator
+    const float *run[kItems];
+    int64_t q[kItems];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float m;
-        if (s == 1)
-            m = px[k];
-        else if (s <= 128 && s >= 8)
-            m = __fdiv_rn(sum_block_le128(px + static_cast<int64_t>(k) * s, s), static_cast<float>(s));
-        else
-            m = __fdiv_rn(pairwise_sum(px + static_cast<int64_t>(k) * s, s), static_cast<float>(s));
-        sum = __dadd_rn(sum, static_cast<double>(m));
+    for (int u = 0; u < kItems; u++) {
+        const int64_t qq = q0 + u / 3;
+        q[u] = qq < npix ? qq : q0;  // an odd tail recomputes pixel q0 (result discarded)
+        run[u] = colors + (u % 3) * cn + q[u] * 4 * s + static_cast<int64_t>(k) * s;
     }
-    double v = __ddiv_rn(sum, 4.0);
-    v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
-    v = __dmul_rn(v, 255.0);
-    const int64_t pix = pix0 + q;
-    const int x = static_cast<int>(pix / h);
-    const int y = static_cast<int>(pix - static_cast<int64_t>(x) * h);
-    const int row = h - 1 - y;
-    image[(static_cast<int64_t>(row) * img_w + (x - x_origin)) * 3 + c] = static_cast<uint8_t>(static_cast<int>(v));
+    float m[kItems];
+    if (s == 1) {
+#pragma unroll
+        for (int u = 0; u < kItems; u++)
+            m[u] = run[u][0];
+    } else {
+        group_pairwise_sum(run, s, j, m);
+#pragma unroll
+        for (int u = 0; u < kItems; u++)
+            m[u] = __fdiv_rn(m[u], static_cast<float>(s));
+    }
+#pragma unroll
+    for (int u = 0; u < kItems; u++) {
+        // the four means live in lanes 0, 8, 16, 24; sum them in binary64 in sub-pixel order
+        const double m0 = static_cast<double>(__shfl_sync(0xffffffffu, m[u], 0));
+        const double m1 = static_cast<double>(__shfl_sync(0xffffffffu, m[u], 8));
+        const double m2 = static_cast<double>(__shfl_sync(0xffffffffu, m[u], 16));
+        const double m3 = static_cast<double>(__shfl_sync(0xffffffffu, m[u], 24));
+        if (lane != u || q0 + u / 3 >= npix)
+            continue;  // lane u writes item u
+        double v = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(m0, m1), m2), m3), 4.0);
+        v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+        v = __dmul_rn(v, 255.0);
+        const int64_t pix = pix0 + q[u];
+        const int x = static_cast<int>(pix / h);
+        const int y = static_cast<int>(pix - static_cast<int64_t>(x) * h);
+        const int row = h - 1 - y;
+        image[(static_cast<int64_t>(row) * img_w + (x - x_origin)) * 3 + (u % 3)] = static_cast<uint8_t>(static_cast<int>(v));
+    }
 }
 
 }  // namespace
@@ -110,7 +154,7 @@ cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *
                            uint8_t *image, int32_t x_origin, int32_t img_w) {
     if (npix <= 0)
         return cudaSuccess;
-    const int64_t blocks = (npix * 3 + 255) / 256;
+    const int64_t blocks = ((npix + 1) / 2 + 7) / 8;  // one warp per 2 pixels, 8 warps per block
     resolve_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(colors, cn, pix0, npix, p.height, p.samples, image, x_origin, img_w);
     return cudaGetLastError();
 }

@@ -1,0 +1,40 @@
+"""Stripe partition of a frame across ranks and assembly of the gathered stripes.
+
+The reference splits the flat, x-major ray array into 8 contiguous slices = vertical stripes
+(src/render.cpp:24-27, scripts/gen_data.py:32); rank r of G renders columns [x0, x1) and the only exchange of
+the whole path is one gather of the resolved 8-bit stripes at the end."""
+
+
+def stripe(width, rank, world):
+    """Columns [x0, x1) of rank `rank`: contiguous, balanced to within one column, covering [0, width)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    base, rem = divmod(width, world)
+    x0 = rank * base + min(rank, rem)
+    return x0, x0 + base + (1 if rank < rem else 0)
+
+
+def path_slice(width, height, samples, rank, world):
+    """[first, first+count) of the N-long path arrays owned by `rank` (contiguous because paths are x-major)."""
+    x0, x1 = stripe(width, rank, world)
+    per_col = height * 4 * samples
+    return x0 * per_col, (x1 - x0) * per_col
+
+
+def gather_stripes(local, width, group=None):
+    """All-gather of per-rank stripes [H, x1-x0, 3] uint8 (torch tensors, any backend) into the full [H, W, 3] frame.
+    Stripes may differ by one column, so each is padded to the widest before the collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    h = local.shape[0]
+    widest = -(-width // world)
+    pad = torch.zeros((h, widest, 3), dtype=local.dtype, device=local.device)
+    pad[:, :local.shape[1]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    frame = torch.empty((h, width, 3), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        x0, x1 = stripe(width, r, world)
+        frame[:, x0:x1] = out[r][:, :x1 - x0]
+    return frame

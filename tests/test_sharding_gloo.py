@@ -1,0 +1,71 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic (stripe partition, slice arithmetic, gather + assembly).
+The per-stripe pixels come from the oracle here (no GPU): what is under test is the sharding, not the kernel."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, w, h, s, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from ascendpathtracing_b200 import sharding
+    from oracle import oracle as O
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x0, x1 = sharding.stripe(w, rank, world)
+        first, count = sharding.path_slice(w, h, s, rank, world)
+        n = w * h * 4 * s
+        # this rank generates and traces ONLY its slice, with the counter-based stream (global path indices)
+        rays = O.gen_rays_from_uniforms(w, h, s, x0, x1, O.philox_uniforms(5, first, count))
+        col = O.trace(rays, O.gen_spheres())
+        # resolve the stripe as its own (x1-x0)-column image: pixels are whole inside a stripe
+        img = O.resolve(col, x1 - x0, h, s) if x1 > x0 else np.zeros((h, 0, 3), np.uint8)
+        frame = sharding.gather_stripes(torch.from_numpy(img), w)
+        if rank == 0:
+            np.save(os.path.join(outdir, "frame.npy"), frame.numpy())
+        assert first + count <= n
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("w,h,s", [(10, 6, 2), (7, 5, 1)])
+def test_two_rank_stripes_assemble_to_the_single_rank_frame(tmp_path, oracle, w, h, s):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, w, h, s, str(tmp_path)), nprocs=2, join=True)
+    frame = np.load(tmp_path / "frame.npy")
+    n = w * h * 4 * s
+    rays = oracle.gen_rays_from_uniforms(w, h, s, 0, w, oracle.philox_uniforms(5, 0, n))
+    whole = oracle.resolve(oracle.trace(rays, oracle.gen_spheres()), w, h, s)
+    assert np.array_equal(frame, whole)
+
+
+def test_stripe_partition_properties():
+    from ascendpathtracing_b200 import sharding
+    for width in (1, 7, 8, 1024, 3840):
+        for world in (1, 2, 3, 4, 8):
+            cols = [sharding.stripe(width, r, world) for r in range(world)]
+            assert cols[0][0] == 0 and cols[-1][1] == width
+            assert all(a[1] == b[0] for a, b in zip(cols, cols[1:]))
+            sizes = [b - a for a, b in cols]
+            assert max(sizes) - min(sizes) <= 1
+            slices = [sharding.path_slice(width, 5, 3, r, world) for r in range(world)]
+            assert sum(c for _, c in slices) == width * 5 * 4 * 3
+    with pytest.raises(ValueError):
+        sharding.stripe(8, 2, 2)
