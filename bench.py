@@ -34,7 +34,8 @@ sys.path.insert(0, ROOT)
 W, H, S, DEPTH, NSPH = 1024, 768, 16, 5, 8
 FLOPS_PER_PATH = DEPTH * (19 * NSPH + 33) + 3  # 928, SURVEY.md 8a/8d
 BYTES_PER_PATH = 36
-CPU_SAMPLE = (1024, 1024, 1, 5)                # 4 194 304 paths of the same scene/camera/depth
+CPU_SAMPLE = (1024, 1024, 1, 5)                # 4 194 304 paths of the same scene/camera/depth (~0.8 s on 8 host threads)
+CPU_SAMPLE_SMALL = (256, 256, 1, 5)            # 262 144 paths: used by --impl reference when --steps is large
 
 
 def peaks():
@@ -93,13 +94,17 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_run(threads):
+_cpu_inputs = {}
+
+
+def cpu_reference_run(threads, sample=CPU_SAMPLE):
     """One pass of the reference's own kernel (oracle/_ref) over the bounded sample. Returns (seconds, paths, kind)."""
     from oracle import oracle as O
-    w, h, s, d = CPU_SAMPLE
+    w, h, s, d = sample
     n = w * h * s * 4
-    rays = O.gen_rays_from_uniforms(w, h, s, 0, w, O.philox_uniforms(1, 0, n))
-    sph = O.gen_spheres()
+    if sample not in _cpu_inputs:  # input generation is not part of the timed pass
+        _cpu_inputs[sample] = (O.gen_rays_from_uniforms(w, h, s, 0, w, O.philox_uniforms(1, 0, n)), O.gen_spheres())
+    rays, sph = _cpu_inputs[sample]
     if O.ref_available(w, h, s, d):
         t = time.perf_counter()
         O.ref_render(rays, sph, w, h, s, d, threads=threads)
@@ -117,21 +122,23 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, emit):
     """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
     cores = host_threads()
     threads = min(8, cores)  # the reference runs 8 blocks (src/main.cpp:18): at most 8-way parallel
+    # bounded sample per step, sized so that the whole run ends within a few minutes whatever --steps is
+    sample = CPU_SAMPLE if (args.steps + args.warmup) <= 120 else CPU_SAMPLE_SMALL
     for _ in range(args.warmup):
-        cpu_reference_run(threads)
+        cpu_reference_run(threads, sample)
     tot_t, tot_n, kind = 0.0, 0, "reference"
     for _ in range(args.steps):
-        t, n, kind = cpu_reference_run(threads)
+        t, n, kind = cpu_reference_run(threads, sample)
         tot_t += t
         tot_n += n
     v = tot_n / tot_t / 1e6
-    w, h, s, d = CPU_SAMPLE
+    w, h, s, d = sample
     line = {"impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -142,7 +149,7 @@ def run_reference_arm(args, rank):
                                        f"compiled -O2 against oracle/shim, {threads} of its 8 blocks in parallel"},
             "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "grays_per_s": v * DEPTH / 1e3}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -160,8 +167,16 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # Exactly ONE line on stdout (the JSON): library chatter such as "NCCL version ..." goes to stderr instead.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, emit)
         return
 
     import torch
@@ -283,7 +298,7 @@ def main():
             w_, h_, s_, _ = CPU_SAMPLE
             line["cpu_baseline"] = {"value": cn / t / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": kind, "host_cores": cores,
                                     "sample": f"{w_}x{h_}x{4 * s_}spp = {cn} paths of the c2 scene/camera, one pass, {t:.2f} s wall"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
