@@ -237,9 +237,10 @@ int ptb200_render_image(const PtParams *p, void *stream_, const uint8_t *spheres
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t spp = 4LL * p->samples;
     const int64_t pix_begin = static_cast<int64_t>(x0) * p->height, pix_end = static_cast<int64_t>(x1) * p->height;
-    // Tile = whole pixels, about 8 Mi paths: rays (24 B) + colours (12 B) per path stay L2/HBM resident between
-    // the three kernels of a tile and never travel to the host.
-    const int64_t target_paths = 8LL << 20;
+    // Tile = whole pixels, up to 64 Mi paths (2.4 GB of workspace: rays 24 B + colours 12 B per path, which stay
+    // in HBM between the three kernels of a tile and never travel to the host).  Large tiles keep the persistent
+    // trace kernel's tail and the launch gaps below a few percent.
+    const int64_t target_paths = 64LL << 20;
     int64_t tile_pix = target_paths / spp;
     if (tile_pix < 1)
         tile_pix = 1;

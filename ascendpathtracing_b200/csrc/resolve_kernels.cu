@@ -14,13 +14,14 @@ namespace ptb200 {
 namespace {
 
 // ---- warp-cooperative form -----------------------------------------------------------------------------
-// One warp resolves kItems (pixel, channel) pairs at a time.  For each pair the 4*S samples are 4 runs of S
+// One warp resolves kItems (pixel, channel) pairs at a time (kPixPerWarp consecutive pixels).  For each pair the 4*S samples are 4 runs of S
 // contiguous floats; eight lanes own one run and play NumPy's eight interleaved accumulators (lane j sums a[j],
 // a[8+j], ... in order), then combine with three xor-shuffles in exactly NumPy's association
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).  Every step of a run reads one full 32-byte sector, and the kItems
 // independent streams keep enough loads in flight to run the colour planes through at HBM speed (a single
 // stream per warp is latency-bound at ~1 TB/s).
-constexpr int kItems = 6;  // 2 pixels x 3 channels
+constexpr int kPixPerWarp = 2;
+constexpr int kItems = 3 * kPixPerWarp;  // pixels x channels resolved concurrently by one warp
 
 __device__ __forceinline__ void group_block_sum(const float *const (&a)[kItems], int64_t off, int n, int j, float (&r)[kItems]) {
     // 8 <= n <= 128; lanes j = 0..7 of the group; results valid in lane j == 0
@@ -103,8 +104,8 @@ __device__ void group_pairwise_sum(const float *const (&a)[kItems], int64_t n, i
 
 __global__ void __launch_bounds__(256) resolve_kernel(const float *__restrict__ colors, int64_t cn, int64_t pix0, int64_t npix, int h, int s,
                                                       uint8_t *__restrict__ image, int x_origin, int img_w) {
-    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // warp = 2 consecutive pixels
-    const int64_t q0 = w * 2;
+    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // warp = kPixPerWarp consecutive pixels
+    const int64_t q0 = w * kPixPerWarp;
     if (q0 >= npix)
         return;  // whole warp
     const int lane = threadIdx.x & 31;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const float *__restrict__ 
 #pragma unroll
     for (int u = 0; u < kItems; u++) {
         const int64_t qq = q0 + u / 3;
-        q[u] = qq < npix ? qq : q0;  // an odd tail recomputes pixel q0 (result discarded)
+        q[u] = qq < npix ? qq : q0;  // a ragged tail recomputes pixel q0 (result discarded)
         run[u] = colors + (u % 3) * cn + q[u] * 4 * s + static_cast<int64_t>(k) * s;
     }
     float m[kItems];
@@ -154,7 +155,7 @@ cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *
                            uint8_t *image, int32_t x_origin, int32_t img_w) {
     if (npix <= 0)
         return cudaSuccess;
-    const int64_t blocks = ((npix + 1) / 2 + 7) / 8;  // one warp per 2 pixels, 8 warps per block
+    const int64_t blocks = ((npix + kPixPerWarp - 1) / kPixPerWarp + 7) / 8;  // 8 warps per block
     resolve_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(colors, cn, pix0, npix, p.height, p.samples, image, x_origin, img_w);
     return cudaGetLastError();
 }

@@ -60,7 +60,7 @@ constexpr int kRing = 32 * kRingBatches;         // ring entries per warp
 constexpr int kWarpsPerBlock = kTraceThreads / 32;
 
 template <int NS, bool EARLY>
-__global__ void __launch_bounds__(kTraceThreads) trace_paths_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
+__global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                     int depth, int nsph, int stride, int light, float scale, float one,
                                                                     unsigned long long *__restrict__ stats) {
     extern __shared__ float4 smem[];

@@ -186,7 +186,7 @@ def test_special_values_in_rays(pt, cuda, oracle):
 
 # ---- ray generation and resolve ------------------------------------------------------------------------
 
-@pytest.mark.parametrize("w,h,s", [(16, 16, 1), (40, 24, 3), (128, 128, 1)])
+@pytest.mark.parametrize("w,h,s", [(16, 16, 1), (40, 24, 3), (128, 128, 1), (517, 389, 2), (1000, 30, 5)])
 def test_gen_rays_mt_replay_bit_exact(pt, cuda, oracle, w, h, s):
     torch = cuda
     p = pt.default_params(width=w, height=h, samples=s)
