@@ -380,3 +380,70 @@ def test_independent_seeds_converge(pt, cuda, oracle):
     assert 14.0 < rmse[16] < 23.0, rmse      # expected 18.3
     assert 7.0 < rmse[64] < 12.0, rmse       # expected 9.4
     assert rmse[64] < 0.62 * rmse[16]        # halves when spp quadruples
+
+
+# ---- the drop-in host and the largest configuration ---------------------------------------------------
+
+def test_host_binary_reproduces_reference_files(pt, cuda, golden_dir, tmp_path):
+    """render_gpu = the reference's src/main.cpp flow on CUDA: --gen replays gen_data.py on the device, the kernel entry is
+    render_do, --ppm replaces data_visualization.py.  All four files must equal what the reference's own pipeline wrote."""
+    import subprocess
+    from ascendpathtracing_b200.host import build as host_build
+    exe = host_build.build()
+    (tmp_path / "input").mkdir()
+    (tmp_path / "output").mkdir()
+    out = subprocess.run([exe, "--gen", "--ppm"], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    for ours, ref in [("input/rays.bin", "w16h16s1d5_rays.bin"), ("input/spheres.bin", "w16h16s1d5_spheres.bin"),
+                      ("output/color.bin", "w16h16s1d5_color.bin"), ("output/color.ppm", "w16h16s1d5_color.ppm")]:
+        assert (tmp_path / ours).read_bytes() == open(os.path.join(golden_dir, ref), "rb").read(), ours
+    # files written by someone else (here: the golden inputs) are read like the reference reads them
+    out = subprocess.run([exe, "--ppm"], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0
+    assert (tmp_path / "output/color.bin").read_bytes() == open(os.path.join(golden_dir, "w16h16s1d5_color.bin"), "rb").read()
+    # a size outside the reference's tiling rule goes through the run-time entry
+    out = subprocess.run([exe, "--gen", "--ppm", "--width", "10", "--height", "6", "--samples", "3"], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert (tmp_path / "output/color.ppm").read_text().startswith("P3\n10 6\n255\n")
+    # missing input -> failure exit code, like run.sh expects (run.sh:124-127)
+    os.remove(tmp_path / "input/rays.bin")
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode != 0
+
+
+def test_c3_full_frame_spot_checks(pt, cuda, oracle):
+    """BASELINE config C3: 3840x2160 at 1024 spp = 8 493 465 600 paths (more than the reference's int32 ray count can
+    hold), rendered through the production entry with the counter-based RNG.  The full-frame oracle is infeasible, so
+    16x16-pixel windows are checked bit for bit: the oracle generates that window's rays from the same global path
+    indices (inputs C3)."""
+    torch = cuda
+    w, h, s, seed = 3840, 2160, 256, 77
+    p = pt.default_params(width=w, height=h, samples=s)
+    d_sph = dev(torch, pt.default_scene())
+    d_stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    # one stripe of 480 columns = what one of 8 GPUs renders; then windows inside it
+    x0, x1 = 1920, 2400
+    d_img = torch.zeros((h, x1 - x0, 3), dtype=torch.uint8, device="cuda")
+    pt.render_image(p, d_sph, d_img, x0=x0, x1=x1, seed=seed, stats=d_stats)
+    img = d_img.cpu().numpy()
+    n_stripe = (x1 - x0) * h * 4 * s
+    assert int(d_stats[0]) == n_stripe == 1061683200
+    per_col = h * 4 * s
+    sph = oracle.gen_spheres()
+    for (wx, wy) in [(1920, 0), (2100, 1000), (2399 - 15, 2160 - 16)]:
+        win = np.zeros((16, 16, 3), dtype=np.uint8)
+        for cx in range(16):
+            x = wx + cx
+            first = x * per_col + wy * 4 * s                 # global path index of pixel (x, wy), sample 0
+            m = 16 * 4 * s                                    # 16 consecutive pixels of this column
+            u = oracle.philox_uniforms(seed, first, m)
+            # rays of pixels (x, wy .. wy+15): the camera formula needs the true (x, y), so generate the whole column
+            # slice through the oracle's column generator and cut the rows out
+            ucol = np.zeros(2 * per_col)
+            ucol[2 * wy * 4 * s:2 * (wy * 4 * s + m)] = u
+            rays = oracle.gen_rays_from_uniforms(w, h, s, x, x + 1, ucol)[:, wy * 4 * s:wy * 4 * s + m]
+            col = oracle.trace(rays, sph)
+            colimg = oracle.resolve(col, 1, 16, s)            # 16 pixels as a 1-column image: row r = y index 15-r
+            win[:, cx] = colimg[:, 0]
+        got = img[h - 1 - (wy + 15):h - 1 - (wy + 15) + 16, wx - x0:wx - x0 + 16]
+        assert np.array_equal(got, win), (wx, wy)
