@@ -25,6 +25,12 @@ class PtParams(ctypes.Structure):
 F_FIXED_DEPTH = 1
 
 
+class PtMaterialParams(ctypes.Structure):
+    """Material extension parameters (include/ptb200.h)."""
+    _fields_ = [("max_depth", ctypes.c_int32), ("rr_start", ctypes.c_int32), ("hit_epsilon", ctypes.c_float), ("reserved", ctypes.c_int32),
+                ("seed", ctypes.c_uint64)]
+
+
 class PtError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"ptb200 error {code}: {msg}")
@@ -74,6 +80,10 @@ def lib():
         "ptb200_resolve": (c.c_int, [PP, vp, vp, i32, i32, vp]),
         "ptb200_render_image": (c.c_int, [PP, vp, vp, vp, u64, i32, i32, vp, vp]),
         "ptb200_render_host": (c.c_int, [PP, vp, vp, vp]),
+        "ptb200_default_material_params": (None, [c.POINTER(PtMaterialParams)]),
+        "render_do_mat": (c.c_int, [PP, c.POINTER(PtMaterialParams), vp, vp, vp, vp, i64, i64, u64, vp]),
+        "ptb200_smallpt_scene": (c.c_int, [vp]),
+        "ptb200_render_image_mat": (c.c_int, [PP, c.POINTER(PtMaterialParams), vp, vp, u64, i32, i32, i32, vp, vp]),
         "ptb200_arena_create": (c.c_int, [sz, c.POINTER(vp)]),
         "ptb200_arena_wrap": (c.c_int, [vp, sz, c.POINTER(vp)]),
         "ptb200_arena_destroy": (c.c_int, [vp]),
@@ -191,6 +201,33 @@ def render_image(p, spheres, image_out, x0=0, x1=None, uniforms=None, seed=0, st
 def render_host(p, rays_host, spheres_host, colors_host):
     """Host buffers (numpy arrays or pinned torch CPU tensors) in and out; synchronous."""
     _check(lib().ptb200_render_host(ctypes.byref(p), _ptr(rays_host), _ptr(spheres_host), _ptr(colors_host)))
+
+
+# ---- material extension ----------------------------------------------------------------------------------
+
+def default_material_params(**over):
+    mp = PtMaterialParams()
+    lib().ptb200_default_material_params(ctypes.byref(mp))
+    for k, v in over.items():
+        setattr(mp, k, v)
+    return mp
+
+
+def smallpt_scene():
+    out = np.zeros(176, dtype=np.float32)
+    _check(lib().ptb200_smallpt_scene(out.ctypes.data))
+    return out
+
+
+def render_do_mat(p, mp, rays, spheres, colors, first=0, count=-1, path0=0, stats=None, stream=None):
+    _check(lib().render_do_mat(ctypes.byref(p), ctypes.byref(mp), _stream_handle(stream), _ptr(rays), _ptr(spheres), _ptr(colors), first, count,
+                               path0, _ptr(stats)))
+
+
+def render_image_mat(p, mp, spheres, image_out, x0=0, x1=None, cam_seed=0, gamma=False, stats=None, stream=None):
+    x1 = p.width if x1 is None else x1
+    _check(lib().ptb200_render_image_mat(ctypes.byref(p), ctypes.byref(mp), _stream_handle(stream), _ptr(spheres), cam_seed, x0, x1,
+                                         1 if gamma else 0, _ptr(image_out), _ptr(stats)))
 
 
 # ---- arena (src/allocator.h) ---------------------------------------------------------------------------

@@ -221,18 +221,18 @@ int ptb200_resolve(const PtParams *p, void *stream, const float *colors, int32_t
     return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_resolve");
 }
 
-int ptb200_render_image(const PtParams *p, void *stream_, const uint8_t *spheres, const double *uniforms, uint64_t seed, int32_t x0,
-                        int32_t x1, uint8_t *image, uint64_t *stats) {
-    int rc = check_params(p, "ptb200_render_image");
+static int render_image_impl(const char *who, const PtParams *p, const PtMaterialParams *mp, void *stream_, const uint8_t *spheres,
+                             const double *uniforms, uint64_t seed, int32_t x0, int32_t x1, int gamma, uint8_t *image, uint64_t *stats) {
+    int rc = check_params(p, who);
     if (rc != PTB200_OK)
         return rc;
     if (x0 < 0 || x1 > p->width || x0 > x1)
-        return fail(PTB200_EINVAL, "ptb200_render_image: columns [%d, %d) outside [0, %d)", x0, x1, p->width);
+        return fail(PTB200_EINVAL, "%s: columns [%d, %d) outside [0, %d)", who, x0, x1, p->width);
     if (x0 == x1)
         return PTB200_OK;
     if (spheres == nullptr || image == nullptr)
-        return fail(PTB200_EINVAL, "ptb200_render_image: NULL buffer");
-    if ((rc = check_device("ptb200_render_image")) != PTB200_OK)
+        return fail(PTB200_EINVAL, "%s: NULL buffer", who);
+    if ((rc = check_device(who)) != PTB200_OK)
         return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t spp = 4LL * p->samples;
@@ -258,10 +258,10 @@ int ptb200_render_image(const PtParams *p, void *stream_, const uint8_t *spheres
         ptb200_arena_free(arena, cols);
         return PTB200_ENOMEM;
     }
-    PtParams tp = *p;
     cudaError_t e = cudaSuccess;
     if (stats != nullptr)
         e = cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), stream);
+    unsigned long long *seg_stat = stats ? reinterpret_cast<unsigned long long *>(stats) + 1 : nullptr;
     for (int64_t q = pix_begin; q < pix_end && e == cudaSuccess; q += tile_pix) {
         const int64_t npix = (pix_end - q < tile_pix) ? pix_end - q : tile_pix;
         const int64_t m = npix * spp;
@@ -269,10 +269,13 @@ int ptb200_render_image(const PtParams *p, void *stream_, const uint8_t *spheres
         if ((e = gen_rays(stream, *p, u, seed, q * spp, m, rays)) != cudaSuccess)
             break;
         // the tile is its own m-path problem for the trace kernel
-        if ((e = trace_paths(stream, tp, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m,
-                             stats ? reinterpret_cast<unsigned long long *>(stats) + 1 : nullptr)) != cudaSuccess)
+        if (mp != nullptr)
+            e = trace_materials(stream, *p, *mp, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m, static_cast<uint64_t>(q * spp), seg_stat);
+        else
+            e = trace_paths(stream, *p, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m, seg_stat);
+        if (e != cudaSuccess)
             break;
-        if ((e = resolve_pixels(stream, *p, cols, m, q, npix, image, x0, x1 - x0)) != cudaSuccess)
+        if ((e = resolve_pixels(stream, *p, cols, m, q, npix, image, x0, x1 - x0, gamma)) != cudaSuccess)
             break;
     }
     const unsigned long long total = static_cast<unsigned long long>((pix_end - pix_begin) * spp);
@@ -284,7 +287,77 @@ int ptb200_render_image(const PtParams *p, void *stream_, const uint8_t *spheres
     ptb200_arena_free(arena, cols);
     if (e == cudaSuccess)
         e = es;
-    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_render_image");
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, who);
+}
+
+int ptb200_render_image(const PtParams *p, void *stream, const uint8_t *spheres, const double *uniforms, uint64_t seed, int32_t x0,
+                        int32_t x1, uint8_t *image, uint64_t *stats) {
+    return render_image_impl("ptb200_render_image", p, nullptr, stream, spheres, uniforms, seed, x0, x1, 0, image, stats);
+}
+
+static int check_material_params(const PtMaterialParams *mp, const char *who) {
+    if (mp == nullptr)
+        return fail(PTB200_EINVAL, "%s: material params is NULL", who);
+    if (mp->max_depth < 1 || mp->rr_start < 0 || !(mp->hit_epsilon > 0.0f))
+        return fail(PTB200_EINVAL, "%s: need max_depth >= 1, rr_start >= 0, hit_epsilon > 0", who);
+    return PTB200_OK;
+}
+
+int ptb200_render_image_mat(const PtParams *p, const PtMaterialParams *mp, void *stream, const uint8_t *spheres, uint64_t cam_seed, int32_t x0,
+                            int32_t x1, int32_t gamma, uint8_t *image, uint64_t *stats) {
+    int rc = check_material_params(mp, "ptb200_render_image_mat");
+    if (rc != PTB200_OK)
+        return rc;
+    return render_image_impl("ptb200_render_image_mat", p, mp, stream, spheres, nullptr, cam_seed, x0, x1, gamma, image, stats);
+}
+
+void ptb200_default_material_params(PtMaterialParams *mp) {
+    if (mp == nullptr)
+        return;
+    const PtMaterialParams d = {64, 5, 0.1f, 0, 0};
+    *mp = d;
+}
+
+int render_do_mat(const PtParams *p, const PtMaterialParams *mp, void *stream, const uint8_t *rays, const uint8_t *spheres, uint8_t *colors,
+                  int64_t first, int64_t count, uint64_t path0, uint64_t *stats) {
+    int rc = check_params(p, "render_do_mat");
+    if (rc != PTB200_OK)
+        return rc;
+    if ((rc = check_material_params(mp, "render_do_mat")) != PTB200_OK)
+        return rc;
+    const int64_t n = total_paths(*p);
+    if (count < 0)
+        count = n - first;
+    if (first < 0 || first + count > n)
+        return fail(PTB200_EINVAL, "render_do_mat: slice [%lld, %lld) outside [0, %lld)", static_cast<long long>(first),
+                    static_cast<long long>(first + count), static_cast<long long>(n));
+    if (count == 0)
+        return PTB200_OK;
+    if (rays == nullptr || spheres == nullptr || colors == nullptr)
+        return fail(PTB200_EINVAL, "render_do_mat: NULL buffer");
+    if ((rc = check_device("render_do_mat")) != PTB200_OK)
+        return rc;
+    cudaError_t e = trace_materials(static_cast<cudaStream_t>(stream), *p, *mp, reinterpret_cast<const float *>(rays),
+                                    reinterpret_cast<const float *>(spheres), reinterpret_cast<float *>(colors), n, first, count, path0,
+                                    reinterpret_cast<unsigned long long *>(stats));
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "render_do_mat");
+}
+
+int ptb200_smallpt_scene(float *out) {
+    if (out == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_smallpt_scene: NULL output");
+    // smallpt's table as quoted in scripts/gen_data.py:77-89: radius, centre, emission, colour, material (0 DIFF, 1 SPEC, 2 REFR)
+    static const double tbl[9][11] = {
+        {1e5, 1e5 + 1, 40.8, 81.6, 0, 0, 0, .75, .25, .25, 0},   {1e5, -1e5 + 99, 40.8, 81.6, 0, 0, 0, .25, .25, .75, 0},
+        {1e5, 50, 40.8, 1e5, 0, 0, 0, .75, .75, .75, 0},         {1e5, 50, 40.8, -1e5 + 170, 0, 0, 0, 0, 0, 0, 0},
+        {1e5, 50, 1e5, 81.6, 0, 0, 0, .75, .75, .75, 0},         {1e5, 50, -1e5 + 81.6, 81.6, 0, 0, 0, .75, .75, .75, 0},
+        {16.5, 27, 16.5, 47, 0, 0, 0, .999, .999, .999, 1},      {16.5, 73, 16.5, 78, 0, 0, 0, .999, .999, .999, 2},
+        {600, 50, 681.6 - .27, 81.6, 12, 12, 12, 0, 0, 0, 0}};
+    memset(out, 0, 176 * sizeof(float));
+    for (int i = 0; i < 9; i++)
+        for (int m = 0; m < 11; m++)
+            out[m * 16 + i] = static_cast<float>(m == 0 ? tbl[i][m] * tbl[i][m] : tbl[i][m]);
+    return PTB200_OK;
 }
 
 int ptb200_render_host(const PtParams *p, const float *rays_host, const float *spheres_host, float *colors_host) {

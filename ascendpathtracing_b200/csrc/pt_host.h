@@ -15,6 +15,11 @@ constexpr int kTraceThreads = 256;
 cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *rays, const float *spheres, float *colors, int64_t n,
                         int64_t first, int64_t count, unsigned long long *stats);
 
+// trace_kernels.cu -- material extension (pt_material.cuh): spheres is the 11-row SoA; element i of the slice has RNG
+// path index path0 + (i - first).
+cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMaterialParams &mp, const float *rays, const float *spheres,
+                            float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats);
+
 // raygen_kernels.cu -- camera rays of the path range [path0, path0+m) of a W x H x S image into an
 // SoA [6][m] buffer.  uniforms (nullable): 2 doubles per ray, uniforms[0] belongs to path0.
 cudaError_t gen_rays(cudaStream_t stream, const PtParams &p, const double *uniforms, uint64_t seed, int64_t path0, int64_t m,
@@ -24,7 +29,7 @@ cudaError_t gen_rays(cudaStream_t stream, const PtParams &p, const double *unifo
 // [3][cn] whose element 0 is the first sample of pixel `pix0`; image points at the full
 // [H][img_w][3] output whose column 0 is image column x_origin.
 cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *colors, int64_t cn, int64_t pix0, int64_t npix,
-                           uint8_t *image, int32_t x_origin, int32_t img_w);
+                           uint8_t *image, int32_t x_origin, int32_t img_w, int gamma = 0);
 
 // fp32_peak.cu
 cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms);

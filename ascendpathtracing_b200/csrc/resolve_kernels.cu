@@ -103,7 +103,7 @@ __device__ void group_pairwise_sum(const float *const (&a)[kItems], int64_t n, i
 }
 
 __global__ void __launch_bounds__(256) resolve_kernel(const float *__restrict__ colors, int64_t cn, int64_t pix0, int64_t npix, int h, int s,
-                                                      uint8_t *__restrict__ image, int x_origin, int img_w) {
+                                                      uint8_t *__restrict__ image, int x_origin, int img_w, int gamma) {
     const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // warp = kPixPerWarp consecutive pixels
     const int64_t q0 = w * kPixPerWarp;
     if (q0 >= npix)
@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(const float *__restrict__ 
             continue;  // lane u writes item u
         double v = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(m0, m1), m2), m3), 4.0);
         v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
-        v = __dmul_rn(v, 255.0);
+        if (gamma)  // smallpt's display transform (material extension only; the reference has no gamma)
+            v = pow(v, 1.0 / 2.2) * 255.0 + 0.5;
+        else
+            v = __dmul_rn(v, 255.0);
         const int64_t pix = pix0 + q[u];
         const int x = static_cast<int>(pix / h);
         const int y = static_cast<int>(pix - static_cast<int64_t>(x) * h);
@@ -152,11 +155,11 @@ __global__ void __launch_bounds__(256) resolve_kernel(const float *__restrict__ 
 }  // namespace
 
 cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *colors, int64_t cn, int64_t pix0, int64_t npix,
-                           uint8_t *image, int32_t x_origin, int32_t img_w) {
+                           uint8_t *image, int32_t x_origin, int32_t img_w, int gamma) {
     if (npix <= 0)
         return cudaSuccess;
     const int64_t blocks = ((npix + kPixPerWarp - 1) / kPixPerWarp + 7) / 8;  // 8 warps per block
-    resolve_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(colors, cn, pix0, npix, p.height, p.samples, image, x_origin, img_w);
+    resolve_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(colors, cn, pix0, npix, p.height, p.samples, image, x_origin, img_w, gamma);
     return cudaGetLastError();
 }
 

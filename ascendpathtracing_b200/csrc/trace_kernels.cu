@@ -13,6 +13,7 @@
 
 #include "pt_device.cuh"
 #include "pt_host.h"
+#include "pt_material.cuh"
 
 namespace ptb200 {
 
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const Tra
         }
         float tmin;
         int idx;
-        nearest_hit<NS>(p, nsph, one, tmin, idx);
+        nearest_hit<NS>(p, nsph, one, kEps, tmin, idx);
         bounce_and_shade<EARLY>(p, tmin, idx, light, sh);
         bounce++;
         want = active && ((bounce >= depth) || (EARLY && path_settled(p, zero_stop)));
@@ -161,6 +162,103 @@ __global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const Tra
         for (int o = 16; o > 0; o >>= 1)
             w += __shfl_xor_sync(0xffffffffu, w, o);
         if ((threadIdx.x & 31) == 0)
+            atomicAdd(stats, static_cast<unsigned long long>(w));
+    }
+}
+
+
+// ---- material extension kernel (pt_material.cuh) ------------------------------------------------------------------
+// Same persistent warps, ring and ballot-ranked regeneration; one iteration = one bounce of material_bounce().
+template <int NS>
+__global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
+                                                                           int max_depth, int rr_start, int nsph, int stride, float eps, float one,
+                                                                           unsigned long long seed, unsigned long long path0,
+                                                                           unsigned long long *__restrict__ stats) {
+    extern __shared__ float4 smem[];
+    MatShared sh;
+    stage_materials_shared(smem, spheres, nsph, stride, sh);
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int warp_in_block = threadIdx.x >> 5;
+    const unsigned int warp = blockIdx.x * kWarpsPerBlock + warp_in_block;
+    const unsigned int nwarps = gridDim.x * kWarpsPerBlock;
+    const unsigned int per = ((count + nwarps - 1) / nwarps + 31u) & ~31u;
+    const unsigned long long wb = static_cast<unsigned long long>(warp) * per;
+    const unsigned int wbeg = wb < count ? static_cast<unsigned int>(wb) : count;
+    const unsigned int wcount = (count - wbeg) < per ? (count - wbeg) : per;
+    float *ring = reinterpret_cast<float *>(smem + 3 * nsph) + warp_in_block * (6 * kRing);
+
+    auto issue_batch = [&](unsigned int b) {
+        const unsigned int e = b * 32u + lane;
+        if (e < wcount) {
+            const unsigned int s = e & (kRing - 1);
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+                __pipeline_memcpy_async(ring + c * kRing + s, pl.ray[c] + wbeg + e, sizeof(float));
+        }
+        __pipeline_commit();
+    };
+    unsigned int issued = 0;
+    for (; issued < kRingBatches; issued++)
+        issue_batch(issued);
+
+    MatPath p;
+    p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
+    p.dz = 1.0f;
+    p.tr = p.tg = p.tb = 1.0f;
+    p.lr = p.lg = p.lb = 0.0f;
+    p.depth = 0;
+    unsigned int segs = 0, head = 0, mine = 0;
+    bool active = false, want = true;
+
+    for (;;) {
+        const unsigned int wmask = __ballot_sync(0xffffffffu, want);
+        if (wmask != 0u) {
+            if (active && want) {
+                const unsigned int i = wbeg + mine;
+                pl.col[0][i] = p.lr;
+                pl.col[1][i] = p.lg;
+                pl.col[2][i] = p.lb;
+            }
+            const unsigned int rank = __popc(wmask & ((1u << lane) - 1u));
+            const unsigned int e = head + rank;
+            const bool take = want && e < wcount;
+            __pipeline_wait_prior(1);
+            __syncwarp();
+            if (take) {
+                const unsigned int s = e & (kRing - 1);
+                p.ox = ring[0 * kRing + s], p.oy = ring[1 * kRing + s], p.oz = ring[2 * kRing + s];
+                p.dx = ring[3 * kRing + s], p.dy = ring[4 * kRing + s], p.dz = ring[5 * kRing + s];
+                mine = e;
+            }
+            if (want) {
+                active = take;
+                p.tr = p.tg = p.tb = 1.0f;
+                p.lr = p.lg = p.lb = 0.0f;
+                p.depth = 0;
+                want = false;
+            }
+            head += __popc(wmask);
+            head = head < wcount ? head : wcount;
+            __syncwarp();
+            if (issued < head / 32u + kRingBatches) {
+                issue_batch(issued);
+                issued++;
+            }
+            if (!__any_sync(0xffffffffu, active))
+                break;
+        }
+        if (active) {  // dead lanes of a finished range idle; live ones diverge by material inside
+            segs++;
+            const bool ended = material_bounce<NS>(p, nsph, one, eps, rr_start, seed, path0 + wbeg + mine, sh);
+            want = ended || p.depth >= max_depth;
+        }
+    }
+    if (stats != nullptr) {
+        unsigned int w = segs;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (lane == 0)
             atomicAdd(stats, static_cast<unsigned long long>(w));
     }
 }
@@ -271,6 +369,53 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
                   : launch_trace<0, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats);
     if (e != cudaSuccess)
         return e;
+    if ((e = cudaEventRecord(s->scene_free, stream)) != cudaSuccess)
+        return e;
+    s->last_stream = stream;
+    s->have_last = true;
+    return cudaSuccess;
+}
+
+
+cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMaterialParams &mp, const float *rays, const float *spheres,
+                            float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats) {
+    if (count <= 0)
+        return cudaSuccess;
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceState *s = nullptr;
+    cudaError_t e = ensure_device_state(&s);
+    if (e != cudaSuccess)
+        return e;
+    if (s->have_last && s->last_stream != stream) {
+        if ((e = cudaStreamWaitEvent(stream, s->scene_free, 0)) != cudaSuccess)
+            return e;
+    }
+    pack_scene_kernel<<<1, 128, 0, stream>>>(spheres, p.sphere_count, p.sphere_stride, s->scene_alias, s->zero_ok_alias);
+    if ((e = cudaGetLastError()) != cudaSuccess)
+        return e;
+    const size_t smem = sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
+    int occ = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0>, kTraceThreads, smem)) != cudaSuccess)
+        return e;
+    if (occ < 1)
+        occ = 1;
+    const int64_t cap = static_cast<int64_t>(s->sm_count) * occ;
+    constexpr int64_t kMaxPerLaunch = 1LL << 30;
+    for (int64_t a = first; a < first + count; a += kMaxPerLaunch) {
+        const int64_t m = (first + count - a < kMaxPerLaunch) ? first + count - a : kMaxPerLaunch;
+        TracePlanes pl;
+        for (int c = 0; c < 6; c++)
+            pl.ray[c] = rays + c * n + a;
+        for (int c = 0; c < 3; c++)
+            pl.col[c] = colors + c * n + a;
+        const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
+        const int grid = static_cast<int>(need < cap ? need : cap);
+        trace_materials_kernel<0><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), mp.max_depth, mp.rr_start,
+                                                                         p.sphere_count, p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed,
+                                                                         path0 + static_cast<uint64_t>(a - first), stats);
+        if ((e = cudaGetLastError()) != cudaSuccess)
+            return e;
+    }
     if ((e = cudaEventRecord(s->scene_free, stream)) != cudaSuccess)
         return e;
     s->last_stream = stream;

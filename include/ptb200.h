@@ -130,6 +130,36 @@ PTB200_API int ptb200_resolve(const PtParams *p, void *stream, const float *colo
 PTB200_API int ptb200_render_image(const PtParams *p, void *stream, const uint8_t *spheres, const double *uniforms, uint64_t seed,
                         int32_t x0, int32_t x1, uint8_t *image, uint64_t *stats);
 
+/* ---- material extension (NOT in the reference, parity against this repo's own CPU twin) ---- */
+
+/* DIFF / SPEC / REFR bounce sampling with Russian roulette, "smallpt in binary32" (DESIGN.md section 8).
+ * spheres: float32 SoA [11][stride] = the reference's ten rows + material (0 DIFF, 1 SPEC, 2 REFR); emission rows are used. */
+typedef struct PtMaterialParams {
+    int32_t max_depth;   /* hard cap on bounces per path */
+    int32_t rr_start;    /* Russian roulette from this depth on (smallpt: 5) */
+    float hit_epsilon;   /* self-intersection guard; 0.1 for binary32 with 1e5-radius walls (1e-4 leaks) */
+    int32_t reserved;
+    uint64_t seed;       /* Philox4x32-10 key; counter = (path index, bounce) */
+} PtMaterialParams;
+
+/* Fills *mp with max_depth 64, rr_start 5, hit_epsilon 0.1, seed 0. */
+PTB200_API void ptb200_default_material_params(PtMaterialParams *mp);
+
+/* Traces paths [first, first+count) of the N-path buffers with materials; element i uses RNG path index
+ * path0 + (i - first) (pass the global index of `first` so that stripes and tiles reproduce the whole frame).
+ * stats (device, nullable): number of ray segments traced is ADDED to stats[0]. */
+PTB200_API int render_do_mat(const PtParams *p, const PtMaterialParams *mp, void *stream, const uint8_t *rays, const uint8_t *spheres,
+                  uint8_t *colors, int64_t first, int64_t count, uint64_t path0, uint64_t *stats);
+
+/* HOST helper: smallpt's 9-sphere scene (quoted at scripts/gen_data.py:77-89) as SoA [11][16] = 176 floats. */
+PTB200_API int ptb200_smallpt_scene(float *out176_host);
+
+/* Production composition with materials: generate (counter-based RNG, key = cam_seed), trace, resolve columns [x0, x1).
+ * gamma != 0 applies smallpt's display transform pow(clamp(x), 1/2.2)*255 + 0.5 instead of the reference's
+ * truncating, gamma-free quantiser. stats as in ptb200_render_image. */
+PTB200_API int ptb200_render_image_mat(const PtParams *p, const PtMaterialParams *mp, void *stream, const uint8_t *spheres, uint64_t cam_seed,
+                            int32_t x0, int32_t x1, int32_t gamma, uint8_t *image, uint64_t *stats);
+
 /* ---- whole-job host-buffer entry (what the reference's main() does, src/main.cpp:46-92) --------- */
 
 /* HOST buffers in, HOST buffer out: arena allocation, H2D of rays+spheres, render, D2H of colours,

@@ -49,6 +49,15 @@ def lib():
         L.pto_resolve.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u8p]
         L.pto_mean_f32.restype = ctypes.c_float
         L.pto_mean_f32.argtypes = [_f32p, ctypes.c_int64]
+        L.pm_trace.restype = ctypes.c_uint64
+        L.pm_trace.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                               ctypes.c_uint64, ctypes.c_uint64]
+        L.pm_trace_f64.restype = None
+        L.pm_trace_f64.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64]
+        L.pm_sincos2pi_array.restype = None
+        L.pm_sincos2pi_array.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64]
+        L.pm_smallpt_scene.restype = None
+        L.pm_smallpt_scene.argtypes = [_f32p]
         L.pto_write_ppm.restype = ctypes.c_int
         L.pto_write_ppm.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, _u8p]
         _lib = L
@@ -143,6 +152,38 @@ def resolve(colors, w, h, s):
 def mean_f32(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return np.float32(lib().pto_mean_f32(a, a.size))
+
+
+# ---- material extension (parity unpinned by the reference; see pt_oracle_mat.c) --------------------------------
+def smallpt_scene():
+    out = np.zeros(176, dtype=np.float32)
+    lib().pm_smallpt_scene(out)
+    return out
+
+
+def trace_materials(rays, spheres, nsph, stride, max_depth=64, rr_start=5, eps=0.1, seed=0, path0=0, return_segments=False):
+    rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(6, -1)
+    n = rays.shape[1]
+    colors = np.zeros((3, n), dtype=np.float32)
+    segs = lib().pm_trace(rays.reshape(-1), np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1), colors.reshape(-1), n, nsph, stride,
+                          max_depth, rr_start, eps, seed, path0)
+    return (colors, int(segs)) if return_segments else colors
+
+
+def trace_materials_f64(rays, spheres, nsph, stride, max_depth=64, rr_start=5, seed=0):
+    rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(6, -1)
+    n = rays.shape[1]
+    colors = np.zeros((3, n), dtype=np.float32)
+    lib().pm_trace_f64(rays.reshape(-1), np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1), colors.reshape(-1), n, nsph, stride,
+                       max_depth, rr_start, seed)
+    return colors
+
+
+def sincos2pi(u):
+    u = np.ascontiguousarray(u, dtype=np.float32)
+    s, c = np.zeros_like(u), np.zeros_like(u)
+    lib().pm_sincos2pi_array(u, s, c, u.size)
+    return s, c
 
 
 def write_ppm(path, img):
