@@ -45,11 +45,11 @@ __device__ __forceinline__ float dot_rn(float ax, float ay, float az, float bx, 
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
 }
 
+// v / |v| with IEEE sqrt and divides (the open-coded correctly rounded forms of pt_device.cuh)
 __device__ __forceinline__ void normalize_rn(float &x, float &y, float &z) {
-    const float len = __fsqrt_rn(dot_rn(x, y, z, x, y, z));
-    x = __fdiv_rn(x, len);
-    y = __fdiv_rn(y, len);
-    z = __fdiv_rn(z, len);
+    float ux, uy, uz;
+    normalize_fast<true>(x, y, z, dot_rn(x, y, z, x, y, z), ux, uy, uz);
+    x = ux, y = uy, z = uz;
 }
 
 // sin(2 pi u), cos(2 pi u) for u in [0, 1): nearest quarter turn, exact remainder, fixed polynomials (FMA), rotation.

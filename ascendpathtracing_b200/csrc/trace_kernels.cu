@@ -360,7 +360,11 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
     pack_scene_kernel<<<1, 128, 0, stream>>>(spheres, p.sphere_count, p.sphere_stride, s->scene_alias, s->zero_ok_alias);
     if ((e = cudaGetLastError()) != cudaSuccess)
         return e;
-    const bool early = !(p.flags & PTB200_F_FIXED_DEPTH);
+    // Early termination and the fixed-depth loop give identical bits, so which one runs is a pure performance choice:
+    // lock-step lanes swap paths once per `depth` iterations, regenerating lanes once per iteration.  Measured on B200
+    // (profiles/r1_depth_sweep.md): fixed wins up to depth ~7 (5.85 vs 6.27 ms at depth 5), regeneration beyond
+    // (30.7 vs 133.6 ms at depth 50).
+    const bool early = !(p.flags & PTB200_F_FIXED_DEPTH) && p.depth > 7;
     if (p.sphere_count == 8)
         e = early ? launch_trace<8, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats)
                   : launch_trace<8, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats);
@@ -394,8 +398,10 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMate
     if ((e = cudaGetLastError()) != cudaSuccess)
         return e;
     const size_t smem = sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
+    const bool ten = p.sphere_count == 9 || p.sphere_count == 10;  // smallpt's scene: fully unrolled pairs (index 9 is padding)
     int occ = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0>, kTraceThreads, smem)) != cudaSuccess)
+    if ((e = ten ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<10>, kTraceThreads, smem)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0>, kTraceThreads, smem)) != cudaSuccess)
         return e;
     if (occ < 1)
         occ = 1;
@@ -410,9 +416,14 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMate
             pl.col[c] = colors + c * n + a;
         const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
         const int grid = static_cast<int>(need < cap ? need : cap);
-        trace_materials_kernel<0><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), mp.max_depth, mp.rr_start,
-                                                                         p.sphere_count, p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed,
-                                                                         path0 + static_cast<uint64_t>(a - first), stats);
+        if (ten)
+            trace_materials_kernel<10><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), mp.max_depth, mp.rr_start,
+                                                                              p.sphere_count, p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed,
+                                                                              path0 + static_cast<uint64_t>(a - first), stats);
+        else
+            trace_materials_kernel<0><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), mp.max_depth, mp.rr_start,
+                                                                             p.sphere_count, p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed,
+                                                                             path0 + static_cast<uint64_t>(a - first), stats);
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }

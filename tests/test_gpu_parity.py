@@ -93,7 +93,8 @@ def test_golden_digests_full_device_pipeline(pt, cuda, manifest, golden_dir, nam
 
 # ---- against the oracle on seeded inputs ----------------------------------------------------------------
 
-@pytest.mark.parametrize("w,h,s,depth", [(16, 16, 1, 5), (64, 48, 2, 5), (256, 256, 1, 5), (33, 17, 3, 7), (64, 64, 1, 50), (3, 5, 1, 1)])
+@pytest.mark.parametrize("w,h,s,depth", [(16, 16, 1, 5), (64, 48, 2, 5), (256, 256, 1, 5), (33, 17, 3, 7), (64, 64, 1, 50), (3, 5, 1, 1), (128, 96, 2, 10),
+                                             (64, 48, 2, 8), (256, 256, 1, 12)])
 @pytest.mark.parametrize("fixed_depth", [False, True])
 def test_trace_bit_exact_vs_oracle(pt, cuda, oracle, w, h, s, depth, fixed_depth):
     p = pt.default_params(width=w, height=h, samples=s, depth=depth, flags=1 if fixed_depth else 0)
@@ -258,18 +259,21 @@ def test_render_host_entry(pt, cuda, oracle):
 def test_render_image_counter_rng_and_stats(pt, cuda, oracle):
     torch = cuda
     w, h, s, seed = 40, 24, 4, 99
-    p = pt.default_params(width=w, height=h, samples=s)
-    n = p.n_paths
     d_sph = dev(torch, pt.default_scene())
-    d_img = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
     d_stats = torch.zeros(2, dtype=torch.int64, device="cuda")
-    pt.render_image(p, d_sph, d_img, seed=seed, stats=d_stats)
-    rays = oracle.gen_rays_from_uniforms(w, h, s, 0, w, oracle.philox_uniforms(seed, 0, n))
-    col, live = oracle.trace(rays, oracle.gen_spheres(), return_live=True)
-    assert np.array_equal(d_img.cpu().numpy(), oracle.resolve(col, w, h, s))
-    stats = d_stats.cpu().numpy()
-    assert stats[0] == n
-    assert stats[1] == live      # segments actually traced == the oracle's count of live segments
+    # depth 10: regeneration with exact early termination -> segments traced == the oracle's count of live segments;
+    # depth 5: the library runs the (bit-identical) lock-step loop because it is faster there -> every segment is traced
+    for depth in (10, 5):
+        p = pt.default_params(width=w, height=h, samples=s, depth=depth)
+        n = p.n_paths
+        d_img = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
+        pt.render_image(p, d_sph, d_img, seed=seed, stats=d_stats)
+        rays = oracle.gen_rays_from_uniforms(w, h, s, 0, w, oracle.philox_uniforms(seed, 0, n))
+        col, live = oracle.trace(rays, oracle.gen_spheres(), depth=depth, return_live=True)
+        assert np.array_equal(d_img.cpu().numpy(), oracle.resolve(col, w, h, s))
+        stats = d_stats.cpu().numpy()
+        assert stats[0] == n
+        assert stats[1] == (live if depth > 7 else n * depth)
     # column stripes (the multi-GPU partition) tile the same image
     for x0, x1 in [(0, 7), (7, 25), (25, 40)]:
         d_part = torch.zeros((h, x1 - x0, 3), dtype=torch.uint8, device="cuda")
@@ -339,12 +343,19 @@ def test_c2_full_size_properties(pt, cuda, oracle):
     d_sph = dev(torch, pt.default_scene())
     d_a = torch.empty(3 * n, dtype=torch.float32, device="cuda")
     d_b = torch.empty(3 * n, dtype=torch.float32, device="cuda")
+    # (1) at depth 10, where the library regenerates paths with early termination unless told otherwise
+    p.depth = 10
     pt.render_do_ex(p, d_rays, d_sph, d_a)
     p.flags = 1
     pt.render_do_ex(p, d_rays, d_sph, d_b)
     p.flags = 0
     torch.cuda.synchronize()
     assert torch.equal(d_a.view(torch.int32), d_b.view(torch.int32))
+    idx10 = torch.arange(7, n, 2003, device="cuda")
+    assert np.array_equal(bits(d_a.view(3, n)[:, idx10].cpu().numpy()),
+                          bits(oracle.trace(d_rays.view(6, n)[:, idx10].cpu().numpy(), oracle.gen_spheres(), depth=10)))
+    p.depth = 5
+    pt.render_do_ex(p, d_rays, d_sph, d_a)
     idx = torch.arange(0, n, 503, device="cuda")
     rays_s = d_rays.view(6, n)[:, idx].cpu().numpy()
     got = d_a.view(3, n)[:, idx].cpu().numpy()
