@@ -84,6 +84,13 @@ def lib():
         "render_do_mat": (c.c_int, [PP, c.POINTER(PtMaterialParams), vp, vp, vp, vp, i64, i64, u64, vp]),
         "ptb200_smallpt_scene": (c.c_int, [vp]),
         "ptb200_render_image_mat": (c.c_int, [PP, c.POINTER(PtMaterialParams), vp, vp, u64, i32, i32, i32, vp, vp]),
+        "ptb200_bvh_build": (c.c_int, [vp, i32, i32, vp, c.POINTER(vp)]),
+        "ptb200_bvh_destroy": (c.c_int, [vp]),
+        "ptb200_bvh_info": (c.c_int, [vp, c.POINTER(i32), c.POINTER(i32), c.POINTER(i32), c.POINTER(i32)]),
+        "ptb200_bvh_first_hit": (c.c_int, [vp, vp, vp, i64, c.c_float, vp, vp]),
+        "render_do_mat_bvh": (c.c_int, [PP, c.POINTER(PtMaterialParams), vp, vp, vp, vp, i64, i64, u64, vp]),
+        "ptb200_render_image_mat_bvh": (c.c_int, [PP, c.POINTER(PtMaterialParams), vp, vp, u64, i32, i32, i32, vp, vp]),
+        "ptb200_random_scene": (c.c_int, [i32, u32, i32, vp]),
         "ptb200_arena_create": (c.c_int, [sz, c.POINTER(vp)]),
         "ptb200_arena_wrap": (c.c_int, [vp, sz, c.POINTER(vp)]),
         "ptb200_arena_destroy": (c.c_int, [vp]),
@@ -228,6 +235,54 @@ def render_image_mat(p, mp, spheres, image_out, x0=0, x1=None, cam_seed=0, gamma
     x1 = p.width if x1 is None else x1
     _check(lib().ptb200_render_image_mat(ctypes.byref(p), ctypes.byref(mp), _stream_handle(stream), _ptr(spheres), cam_seed, x0, x1,
                                          1 if gamma else 0, _ptr(image_out), _ptr(stats)))
+
+
+# ---- large scenes: BVH -----------------------------------------------------------------------------------
+
+class Bvh:
+    """Handle of a GPU-built sphere BVH (ptb200_bvh_*)."""
+
+    def __init__(self, spheres, count, stride, stream=None):
+        h = ctypes.c_void_p()
+        _check(lib().ptb200_bvh_build(_ptr(spheres), count, stride, _stream_handle(stream), ctypes.byref(h)))
+        self._h = h
+
+    def info(self):
+        v = [ctypes.c_int32() for _ in range(4)]
+        _check(lib().ptb200_bvh_info(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("spheres", "big", "small", "nodes"), (x.value for x in v)))
+
+    def first_hit(self, rays, n, tmin_out, idx_out, eps=1e-4, stream=None):
+        _check(lib().ptb200_bvh_first_hit(self._h, _stream_handle(stream), _ptr(rays), n, eps, _ptr(tmin_out), _ptr(idx_out)))
+
+    def close(self):
+        if self._h:
+            lib().ptb200_bvh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def random_scene(n_random, seed=12345, stride=None):
+    stride = 7 + n_random if stride is None else stride
+    out = np.zeros(11 * stride, dtype=np.float32)
+    _check(lib().ptb200_random_scene(n_random, seed, stride, out.ctypes.data))
+    return out
+
+
+def render_do_mat_bvh(p, mp, bvh, rays, colors, first=0, count=-1, path0=0, stats=None, stream=None):
+    _check(lib().render_do_mat_bvh(ctypes.byref(p), ctypes.byref(mp), bvh._h, _stream_handle(stream), _ptr(rays), _ptr(colors), first, count, path0,
+                                   _ptr(stats)))
+
+
+def render_image_mat_bvh(p, mp, bvh, image_out, x0=0, x1=None, cam_seed=0, gamma=False, stats=None, stream=None):
+    x1 = p.width if x1 is None else x1
+    _check(lib().ptb200_render_image_mat_bvh(ctypes.byref(p), ctypes.byref(mp), bvh._h, _stream_handle(stream), cam_seed, x0, x1,
+                                             1 if gamma else 0, _ptr(image_out), _ptr(stats)))
 
 
 # ---- arena (src/allocator.h) ---------------------------------------------------------------------------

@@ -1,0 +1,361 @@
+// GPU build of the sphere BVH of pt_bvh.cuh (LBVH: Morton codes -> radix sort -> Karras 2012 hierarchy -> bottom-up
+// boxes), plus the C-ABI handle around it.  The only library call is cub::DeviceRadixSort for the one-time sort of the
+// Morton keys; everything on the per-ray path (traversal, leaf tests) is this repo's code.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "pt_bvh.cuh"
+#include "pt_host.h"
+
+namespace ptb200 {
+
+struct Aabb {
+    float lo[3], hi[3];
+};
+
+namespace {
+
+__device__ __forceinline__ unsigned int expand_bits(unsigned int v) {  // 10 bits -> every third bit
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+// AoS copies of the per-sphere data (original index order) + Morton keys of the small spheres.
+__global__ void prepare_kernel(const float *__restrict__ sph, int n, int stride, float4 *geom, float4 *color, float4 *emission, const int *small_index,
+                               int n_small, float3 lo, float3 inv_extent, unsigned int *keys, int *vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        geom[i] = make_float4(sph[1 * stride + i], sph[2 * stride + i], sph[3 * stride + i], -sph[0 * stride + i]);
+        color[i] = make_float4(sph[7 * stride + i], sph[8 * stride + i], sph[9 * stride + i], sph[10 * stride + i]);
+        emission[i] = make_float4(sph[4 * stride + i], sph[5 * stride + i], sph[6 * stride + i], 0.0f);
+    }
+    if (i < n_small) {
+        const int k = small_index[i];
+        const float x = (sph[1 * stride + k] - lo.x) * inv_extent.x, y = (sph[2 * stride + k] - lo.y) * inv_extent.y,
+                    z = (sph[3 * stride + k] - lo.z) * inv_extent.z;
+        const unsigned int xi = static_cast<unsigned int>(fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f));
+        const unsigned int yi = static_cast<unsigned int>(fminf(fmaxf(y * 1024.0f, 0.0f), 1023.0f));
+        const unsigned int zi = static_cast<unsigned int>(fminf(fmaxf(z * 1024.0f, 0.0f), 1023.0f));
+        keys[i] = (expand_bits(xi) << 2) | (expand_bits(yi) << 1) | expand_bits(zi);
+        vals[i] = k;
+    }
+}
+
+__device__ __forceinline__ int delta(const unsigned int *keys, int n, int i, int j) {
+    if (j < 0 || j >= n)
+        return -1;
+    const unsigned int a = keys[i], b = keys[j];
+    if (a == b)
+        return 32 + __clz(static_cast<unsigned int>(i) ^ static_cast<unsigned int>(j));
+    return __clz(a ^ b);
+}
+
+// Karras 2012, one thread per internal node; leaves are referenced as ~(original sphere index).
+__global__ void hierarchy_kernel(const unsigned int *__restrict__ keys, const int *__restrict__ vals, int n, BvhNode *nodes, int *leaf_parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1)
+        return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin)
+        lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin)
+            l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode)
+            s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    if (lo == gamma) {
+        nodes[i].left = ~vals[gamma];
+        leaf_parent[gamma] = i;
+    } else {
+        nodes[i].left = gamma;
+        nodes[gamma].parent = i;
+    }
+    if (hi == gamma + 1) {
+        nodes[i].right = ~vals[gamma + 1];
+        leaf_parent[gamma + 1] = i;
+    } else {
+        nodes[i].right = gamma + 1;
+        nodes[gamma + 1].parent = i;
+    }
+    if (i == 0)
+        nodes[0].parent = -1;
+}
+
+__device__ __forceinline__ Aabb sphere_box(const float4 g, float e_disc) {
+    const float r2 = -g.w;
+    const float r = sqrtf(fmaxf(r2, 0.0f));
+    const float pad = (sqrtf(r2 + e_disc) - r) + 1e-3f * r + 1e-3f;  // see pt_bvh.cuh
+    Aabb b;
+    b.lo[0] = g.x - r - pad, b.lo[1] = g.y - r - pad, b.lo[2] = g.z - r - pad;
+    b.hi[0] = g.x + r + pad, b.hi[1] = g.y + r + pad, b.hi[2] = g.z + r + pad;
+    return b;
+}
+
+__device__ __forceinline__ Aabb merge(const Aabb &a, const Aabb &b) {
+    Aabb m;
+    for (int c = 0; c < 3; c++) {
+        m.lo[c] = fminf(a.lo[c], b.lo[c]);
+        m.hi[c] = fmaxf(a.hi[c], b.hi[c]);
+    }
+    return m;
+}
+
+// One thread per leaf climbs towards the root; the second thread to reach a node (atomic counter) owns it, so both
+// children are complete by then.  own[] receives every internal node's box.
+__global__ void fit_kernel(const int *__restrict__ vals, const int *__restrict__ leaf_parent, int n, const float4 *__restrict__ geom, float e_disc,
+                           BvhNode *nodes, Aabb *own, unsigned int *visits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    int node = leaf_parent[i];
+    while (node >= 0) {
+        if (atomicAdd(&visits[node], 1u) == 0u)
+            return;  // first arrival: the sibling subtree is not done yet
+        __threadfence();
+        const int l = nodes[node].left, r = nodes[node].right;
+        const Aabb bl = l < 0 ? sphere_box(geom[~l], e_disc) : own[l];
+        const Aabb br = r < 0 ? sphere_box(geom[~r], e_disc) : own[r];
+        nodes[node].a = make_float4(bl.lo[0], bl.lo[1], bl.lo[2], bl.hi[0]);
+        nodes[node].b = make_float4(bl.hi[1], bl.hi[2], br.lo[0], br.lo[1]);
+        nodes[node].c = make_float4(br.lo[2], br.hi[0], br.hi[1], br.hi[2]);
+        own[node] = merge(bl, br);
+        __threadfence();
+        node = nodes[node].parent;
+    }
+}
+
+// Nearest hit only (tests / diagnostics): big spheres brute force + tree, the reference's (t, index) semantics.
+__global__ void first_hit_kernel(BvhScene sc, const float *__restrict__ rays, int64_t n, float eps, float *__restrict__ tmin_out,
+                                 int *__restrict__ idx_out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float ox = rays[i], oy = rays[n + i], oz = rays[2 * n + i], dx = rays[3 * n + i], dy = rays[4 * n + i], dz = rays[5 * n + i];
+    float tmin = kMiss;
+    int idx = 0;
+    for (int k = 0; k < sc.n_big; k++) {
+        const int s = sc.big_index[k];
+        const float4 g = sc.geom[s];
+        const float t = sphere_t(ox, oy, oz, dx, dy, dz, g.x, g.y, g.z, g.w, eps);
+        if (t < tmin) {  // ascending original index: strict < keeps the lowest index on ties
+            tmin = t;
+            idx = s;
+        }
+    }
+    bvh_nearest(sc, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
+    tmin_out[i] = tmin;
+    idx_out[i] = idx;
+}
+
+}  // namespace
+}  // namespace ptb200
+
+using namespace ptb200;
+
+struct PtBvh {
+    int device = 0;
+    int n = 0, stride = 0, n_big = 0, n_small = 0;
+    float e_disc = 0.0f;
+    BvhNode *nodes = nullptr;
+    float4 *geom = nullptr, *color = nullptr, *emission = nullptr;
+    int *big_index = nullptr;
+    float *big_soa = nullptr;  // [11][16] SoA of the big spheres for the constant-bank pack
+    int only_leaf = 0;
+    BvhScene scene() const {
+        BvhScene s;
+        s.nodes = nodes, s.geom = geom, s.color = color, s.emission = emission, s.big_index = big_index;
+        s.n_big = n_big, s.n_small = n_small, s.root = 0, s.only_leaf = only_leaf;
+        return s;
+    }
+};
+
+namespace ptb200 {
+BvhScene bvh_scene(const PtBvh *b) { return b->scene(); }
+const float *bvh_big_soa(const PtBvh *b) { return b->big_soa; }
+int bvh_big_count(const PtBvh *b) { return b->n_big; }
+int bvh_sphere_count(const PtBvh *b) { return b->n; }
+}  // namespace ptb200
+
+extern "C" {
+
+int ptb200_bvh_destroy(PtBvh *b) {
+    if (b == nullptr)
+        return PTB200_OK;
+    cudaFree(b->nodes);
+    cudaFree(b->geom);
+    cudaFree(b->color);
+    cudaFree(b->emission);
+    cudaFree(b->big_index);
+    cudaFree(b->big_soa);
+    delete b;
+    return PTB200_OK;
+}
+
+int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, void *stream_, PtBvh **out) {
+    if (out == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_bvh_build: NULL out");
+    *out = nullptr;
+    if (spheres_ == nullptr || count < 1 || stride < count)
+        return fail(PTB200_EINVAL, "ptb200_bvh_build: need spheres, count >= 1, stride >= count");
+    if (count > (1 << 24))
+        return fail(PTB200_EINVAL, "ptb200_bvh_build: at most 2^24 spheres");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(PTB200_ENODEV, "ptb200_bvh_build: no CUDA device (this library has no CPU fallback)");
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const float *sph = reinterpret_cast<const float *>(spheres_);
+    // Classification and bounds on the host (4 rows of the SoA, 16 bytes per sphere); the tree is built on the device.
+    std::vector<float> rows(static_cast<size_t>(4) * count);
+    cudaError_t e = cudaSuccess;
+    for (int m = 0; m < 4 && e == cudaSuccess; m++)
+        e = cudaMemcpyAsync(rows.data() + static_cast<size_t>(m) * count, sph + static_cast<size_t>(m) * stride, sizeof(float) * count,
+                            cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess)
+        return fail_cuda(e, "ptb200_bvh_build");
+    std::vector<int> big, small;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < count; i++) {
+        const float r2 = rows[i];
+        if (!(r2 < kBigR2)) {  // huge or NaN radius: brute force
+            big.push_back(i);
+            continue;
+        }
+        small.push_back(i);
+        const float r = std::sqrt(std::max(r2, 0.0f));
+        for (int c = 0; c < 3; c++) {
+            const float v = rows[static_cast<size_t>(1 + c) * count + i];
+            lo[c] = std::min(lo[c], v - r);
+            hi[c] = std::max(hi[c], v + r);
+        }
+    }
+    if (big.size() > 1024)
+        return fail(PTB200_EINVAL, "ptb200_bvh_build: %zu spheres of radius >= 100 (at most 1024 fit the brute-force list)", big.size());
+    PtBvh *b = new PtBvh();
+    cudaGetDevice(&b->device);
+    b->n = count, b->stride = stride, b->n_big = static_cast<int>(big.size()), b->n_small = static_cast<int>(small.size());
+    double diag2 = 0.0;
+    float ext[3] = {1.0f, 1.0f, 1.0f};
+    if (!small.empty())
+        for (int c = 0; c < 3; c++) {
+            const double dlt = static_cast<double>(hi[c]) - lo[c];
+            diag2 += dlt * dlt;
+            ext[c] = static_cast<float>(dlt > 0 ? dlt : 1.0);
+        }
+    b->e_disc = static_cast<float>(diag2 * (1.0 / 524288.0));  // 2^-19 D^2
+
+    auto dmalloc = [&](void **p, size_t bytes) { return e == cudaSuccess ? (e = cudaMalloc(p, bytes ? bytes : 16)) : e; };
+    int *d_small = nullptr, *d_vals_in = nullptr, *d_vals = nullptr, *d_leaf_parent = nullptr;
+    unsigned int *d_keys_in = nullptr, *d_keys = nullptr, *d_visits = nullptr;
+    Aabb *d_own = nullptr;
+    void *d_tmp = nullptr;
+    const int ns = b->n_small, nb = b->n_big;
+    dmalloc(reinterpret_cast<void **>(&b->geom), sizeof(float4) * count);
+    dmalloc(reinterpret_cast<void **>(&b->color), sizeof(float4) * count);
+    dmalloc(reinterpret_cast<void **>(&b->emission), sizeof(float4) * count);
+    dmalloc(reinterpret_cast<void **>(&b->big_index), sizeof(int) * std::max(nb, 1));
+    dmalloc(reinterpret_cast<void **>(&b->big_soa), sizeof(float) * 11 * 1024);
+    dmalloc(reinterpret_cast<void **>(&b->nodes), sizeof(BvhNode) * std::max(ns - 1, 1));
+    dmalloc(reinterpret_cast<void **>(&d_small), sizeof(int) * std::max(ns, 1));
+    dmalloc(reinterpret_cast<void **>(&d_keys_in), sizeof(unsigned int) * std::max(ns, 1));
+    dmalloc(reinterpret_cast<void **>(&d_keys), sizeof(unsigned int) * std::max(ns, 1));
+    dmalloc(reinterpret_cast<void **>(&d_vals_in), sizeof(int) * std::max(ns, 1));
+    dmalloc(reinterpret_cast<void **>(&d_vals), sizeof(int) * std::max(ns, 1));
+    dmalloc(reinterpret_cast<void **>(&d_leaf_parent), sizeof(int) * std::max(ns, 1));
+    dmalloc(reinterpret_cast<void **>(&d_visits), sizeof(unsigned int) * std::max(ns, 1));
+    dmalloc(reinterpret_cast<void **>(&d_own), sizeof(Aabb) * std::max(ns, 1));
+    if (e == cudaSuccess && nb > 0)
+        e = cudaMemcpyAsync(b->big_index, big.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && ns > 0)
+        e = cudaMemcpyAsync(d_small, small.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, stream);
+    // compacted SoA of the big spheres, stride 1024 rows of the 11-row layout, for pack_scene_kernel / shared staging
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(b->big_soa, 0, sizeof(float) * 11 * 1024, stream);
+    for (int k = 0; k < nb && e == cudaSuccess; k++)
+        e = cudaMemcpy2DAsync(b->big_soa + k, sizeof(float) * 1024, sph + big[k], sizeof(float) * stride, sizeof(float), 11, cudaMemcpyDeviceToDevice,
+                              stream);
+    if (e == cudaSuccess) {
+        const int threads = 256, blocks = (std::max(count, ns) + threads - 1) / threads;
+        prepare_kernel<<<blocks, threads, 0, stream>>>(sph, count, stride, b->geom, b->color, b->emission, d_small, ns, make_float3(lo[0], lo[1], lo[2]),
+                                                       make_float3(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]), d_keys_in, d_vals_in);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && ns == 1) {
+        b->only_leaf = ~small[0];
+    }
+    if (e == cudaSuccess && ns >= 2) {
+        size_t tmp_bytes = 0;
+        e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys_in, d_keys, d_vals_in, d_vals, ns, 0, 30, stream);
+        if (e == cudaSuccess)
+            e = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
+        if (e == cudaSuccess)
+            e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys_in, d_keys, d_vals_in, d_vals, ns, 0, 30, stream);
+        if (e == cudaSuccess)
+            e = cudaMemsetAsync(d_visits, 0, sizeof(unsigned int) * ns, stream);
+        if (e == cudaSuccess) {
+            hierarchy_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(d_keys, d_vals, ns, b->nodes, d_leaf_parent);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) {
+            fit_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(d_vals, d_leaf_parent, ns, b->geom, b->e_disc, b->nodes, d_own, d_visits);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(stream);
+    cudaFree(d_small), cudaFree(d_keys_in), cudaFree(d_keys), cudaFree(d_vals_in), cudaFree(d_vals), cudaFree(d_leaf_parent), cudaFree(d_visits),
+        cudaFree(d_own), cudaFree(d_tmp);
+    if (e != cudaSuccess) {
+        ptb200_bvh_destroy(b);
+        return e == cudaErrorMemoryAllocation ? fail(PTB200_ENOMEM, "ptb200_bvh_build: out of device memory") : fail_cuda(e, "ptb200_bvh_build");
+    }
+    *out = b;
+    return PTB200_OK;
+}
+
+int ptb200_bvh_info(const PtBvh *b, int32_t *n_spheres, int32_t *n_big, int32_t *n_small, int32_t *n_nodes) {
+    if (b == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_bvh_info: NULL handle");
+    if (n_spheres)
+        *n_spheres = b->n;
+    if (n_big)
+        *n_big = b->n_big;
+    if (n_small)
+        *n_small = b->n_small;
+    if (n_nodes)
+        *n_nodes = b->n_small > 1 ? b->n_small - 1 : 0;
+    return PTB200_OK;
+}
+
+int ptb200_bvh_first_hit(const PtBvh *b, void *stream, const float *rays, int64_t n, float eps, float *tmin_out, int32_t *idx_out) {
+    if (b == nullptr || rays == nullptr || tmin_out == nullptr || idx_out == nullptr || n < 0)
+        return fail(PTB200_EINVAL, "ptb200_bvh_first_hit: bad argument");
+    if (n == 0)
+        return PTB200_OK;
+    first_hit_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(b->scene(), rays, n, eps, tmin_out,
+                                                                                                         idx_out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_bvh_first_hit");
+}
+
+}  // extern "C"

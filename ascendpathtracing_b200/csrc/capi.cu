@@ -222,7 +222,8 @@ int ptb200_resolve(const PtParams *p, void *stream, const float *colors, int32_t
 }
 
 static int render_image_impl(const char *who, const PtParams *p, const PtMaterialParams *mp, void *stream_, const uint8_t *spheres,
-                             const double *uniforms, uint64_t seed, int32_t x0, int32_t x1, int gamma, uint8_t *image, uint64_t *stats) {
+                             const double *uniforms, uint64_t seed, int32_t x0, int32_t x1, int gamma, uint8_t *image, uint64_t *stats,
+                             const PtBvh *tree = nullptr) {
     int rc = check_params(p, who);
     if (rc != PTB200_OK)
         return rc;
@@ -230,7 +231,7 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
         return fail(PTB200_EINVAL, "%s: columns [%d, %d) outside [0, %d)", who, x0, x1, p->width);
     if (x0 == x1)
         return PTB200_OK;
-    if (spheres == nullptr || image == nullptr)
+    if ((spheres == nullptr && tree == nullptr) || image == nullptr)
         return fail(PTB200_EINVAL, "%s: NULL buffer", who);
     if ((rc = check_device(who)) != PTB200_OK)
         return rc;
@@ -270,7 +271,8 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
             break;
         // the tile is its own m-path problem for the trace kernel
         if (mp != nullptr)
-            e = trace_materials(stream, *p, *mp, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m, static_cast<uint64_t>(q * spp), seg_stat);
+            e = trace_materials(stream, *p, *mp, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m, static_cast<uint64_t>(q * spp), seg_stat,
+                                tree);
         else
             e = trace_paths(stream, *p, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m, seg_stat);
         if (e != cudaSuccess)
@@ -341,6 +343,83 @@ int render_do_mat(const PtParams *p, const PtMaterialParams *mp, void *stream, c
                                     reinterpret_cast<const float *>(spheres), reinterpret_cast<float *>(colors), n, first, count, path0,
                                     reinterpret_cast<unsigned long long *>(stats));
     return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "render_do_mat");
+}
+
+// check_params with the sphere fields neutralised: with a tree the scene comes from the handle
+static PtParams with_tree_params(const PtParams *p) {
+    PtParams q = *p;
+    q.sphere_count = 1;
+    q.sphere_stride = 1;
+    return q;
+}
+
+int render_do_mat_bvh(const PtParams *p, const PtMaterialParams *mp, const PtBvh *bvh, void *stream, const uint8_t *rays, uint8_t *colors,
+                      int64_t first, int64_t count, uint64_t path0, uint64_t *stats) {
+    if (p == nullptr || bvh == nullptr)
+        return fail(PTB200_EINVAL, "render_do_mat_bvh: NULL params or tree");
+    const PtParams q = with_tree_params(p);
+    int rc = check_params(&q, "render_do_mat_bvh");
+    if (rc != PTB200_OK)
+        return rc;
+    if ((rc = check_material_params(mp, "render_do_mat_bvh")) != PTB200_OK)
+        return rc;
+    const int64_t n = total_paths(q);
+    if (count < 0)
+        count = n - first;
+    if (first < 0 || first + count > n)
+        return fail(PTB200_EINVAL, "render_do_mat_bvh: slice outside [0, %lld)", static_cast<long long>(n));
+    if (count == 0)
+        return PTB200_OK;
+    if (rays == nullptr || colors == nullptr)
+        return fail(PTB200_EINVAL, "render_do_mat_bvh: NULL buffer");
+    if ((rc = check_device("render_do_mat_bvh")) != PTB200_OK)
+        return rc;
+    cudaError_t e = trace_materials(static_cast<cudaStream_t>(stream), q, *mp, reinterpret_cast<const float *>(rays), nullptr,
+                                    reinterpret_cast<float *>(colors), n, first, count, path0, reinterpret_cast<unsigned long long *>(stats), bvh);
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "render_do_mat_bvh");
+}
+
+int ptb200_render_image_mat_bvh(const PtParams *p, const PtMaterialParams *mp, const PtBvh *bvh, void *stream, uint64_t cam_seed, int32_t x0,
+                                int32_t x1, int32_t gamma, uint8_t *image, uint64_t *stats) {
+    if (p == nullptr || bvh == nullptr)
+        return fail(PTB200_EINVAL, "ptb200_render_image_mat_bvh: NULL params or tree");
+    int rc = check_material_params(mp, "ptb200_render_image_mat_bvh");
+    if (rc != PTB200_OK)
+        return rc;
+    const PtParams q = with_tree_params(p);
+    return render_image_impl("ptb200_render_image_mat_bvh", &q, mp, stream, nullptr, nullptr, cam_seed, x0, x1, gamma, image, stats, bvh);
+}
+
+int ptb200_random_scene(int32_t n_random, uint32_t seed, int32_t stride, float *out) {
+    if (out == nullptr || n_random < 0 || stride < 7 + n_random)
+        return fail(PTB200_EINVAL, "ptb200_random_scene: need out, n_random >= 0, stride >= 7 + n_random");
+    const size_t total = static_cast<size_t>(11) * stride;
+    memset(out, 0, total * sizeof(float));
+    // scripts/gen_data.py:94-102 without the mirror ball: six walls (DIFF) and the light
+    static const double base[7][11] = {
+        {1e5, 1e5 + 1, 40.8, 81.6, 0, 0, 0, 0.435, 0.376, 0.667, 0},  {1e5, -1e5 + 99, 40.8, 81.6, 0, 0, 0, 0.667, 0.129, 0.086, 0},
+        {1e5, 50, 40.8, 1e5, 0, 0, 0, 0.270, 0.725, 0.486, 0},        {1e5, 50, 40.8, -1e5 + 170, 0, 0, 0, 0, 0, 0, 0},
+        {1e5, 50, 1e5, 81.6, 0, 0, 0, 0.5, 0.5, 0.5, 0},              {1e5, 50, -1e5 + 81.6, 81.6, 0, 0, 0, 0.141, 0.408, 0.635, 0},
+        {600, 50, 681.6 - 0.27, 81.6, 12, 12, 12, 0, 0, 0, 0}};
+    for (int i = 0; i < 7; i++)
+        for (int m = 0; m < 11; m++)
+            out[static_cast<size_t>(m) * stride + i] = static_cast<float>(m == 0 ? base[i][m] * base[i][m] : base[i][m]);
+    std::vector<double> u(static_cast<size_t>(8) * n_random);
+    int rc = ptb200_mt19937_uniforms(seed, 0, u.size(), u.data());
+    if (rc != PTB200_OK)
+        return rc;
+    for (int k = 0; k < n_random; k++) {
+        const double *q = u.data() + static_cast<size_t>(8) * k;
+        const int i = 7 + k;
+        const double r = 0.2 + 0.8 * q[3];
+        int mat = static_cast<int>(3.0 * q[4]);
+        mat = mat > 2 ? 2 : mat;
+        const double v[11] = {r * r, 1.0 + 98.0 * q[0], 81.6 * q[1], 170.0 * q[2], 0, 0, 0, 0.2 + 0.75 * q[5], 0.2 + 0.75 * q[6], 0.2 + 0.75 * q[7],
+                              static_cast<double>(mat)};
+        for (int m = 0; m < 11; m++)
+            out[static_cast<size_t>(m) * stride + i] = static_cast<float>(v[m]);
+    }
+    return PTB200_OK;
 }
 
 int ptb200_smallpt_scene(float *out) {

@@ -17,8 +17,17 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
 
 // trace_kernels.cu -- material extension (pt_material.cuh): spheres is the 11-row SoA; element i of the slice has RNG
 // path index path0 + (i - first).
+// tree (nullable): a BVH built by ptb200_bvh_build over the same spheres; then `spheres` may be NULL.
 cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMaterialParams &mp, const float *rays, const float *spheres,
-                            float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats);
+                            float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats,
+                            const PtBvh *tree = nullptr);
+
+// bvh.cu
+struct BvhScene;
+BvhScene bvh_scene(const PtBvh *b);
+const float *bvh_big_soa(const PtBvh *b);
+int bvh_big_count(const PtBvh *b);
+int bvh_sphere_count(const PtBvh *b);
 
 // raygen_kernels.cu -- camera rays of the path range [path0, path0+m) of a W x H x S image into an
 // SoA [6][m] buffer.  uniforms (nullable): 2 doubles per ray, uniforms[0] belongs to path0.

@@ -10,6 +10,7 @@
 // of the warp ends.
 #pragma once
 #include "philox.h"
+#include "pt_bvh.cuh"
 #include "pt_device.cuh"
 
 namespace ptb200 {
@@ -72,14 +73,27 @@ __device__ __forceinline__ void sincos2pi(float u, float &s_out, float &c_out) {
 }
 
 // One bounce.  Returns true when the path has ended (its radiance is final).
-template <int NS>
+// BVH = false: all spheres in the constant bank (nsph of them), per-sphere data from shared memory.
+// BVH = true : the constant bank holds only the huge spheres (nsph = their count, indices through bvh.big_index), the rest
+//              is found through the tree; per-sphere data comes from global memory by original index.
+template <int NS, bool BVH>
 __device__ __forceinline__ bool material_bounce(MatPath &p, int nsph, float one, float eps, int rr_start, unsigned long long seed,
-                                                unsigned long long path, const MatShared &sh) {
+                                                unsigned long long path, const MatShared &sh, const BvhScene &bvh) {
     PathState ray;
     ray.ox = p.ox, ray.oy = p.oy, ray.oz = p.oz, ray.dx = p.dx, ray.dy = p.dy, ray.dz = p.dz;
     float tmin;
     int idx;
-    nearest_hit<NS>(ray, nsph, one, eps, tmin, idx);
+    if (BVH) {
+        tmin = kMiss;
+        idx = 0;
+        if (nsph > 0) {
+            nearest_hit<0>(ray, nsph, one, eps, tmin, idx);
+            idx = (tmin < kMiss) ? __ldg(bvh.big_index + idx) : 0;
+        }
+        bvh_nearest(bvh, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, eps, tmin, idx);
+    } else {
+        nearest_hit<NS>(ray, nsph, one, eps, tmin, idx);
+    }
     if (!(tmin < kMiss))
         return true;
     uint32_t w[4] = {static_cast<uint32_t>(path), static_cast<uint32_t>(path >> 32), static_cast<uint32_t>(p.depth), 0x4d41u};
@@ -87,9 +101,17 @@ __device__ __forceinline__ bool material_bounce(MatPath &p, int nsph, float one,
     const float u1 = __fmul_rn(static_cast<float>(w[0] >> 8), 5.9604645e-8f), u2 = __fmul_rn(static_cast<float>(w[1] >> 8), 5.9604645e-8f);
     const float u3 = __fmul_rn(static_cast<float>(w[2] >> 8), 5.9604645e-8f), u4 = __fmul_rn(static_cast<float>(w[3] >> 8), 5.9604645e-8f);
 
-    const float4 ctr = sh.center[idx];
-    const float4 col = sh.color[idx];
-    const float4 emi = sh.emission[idx];
+    float4 ctr, col, emi;
+    if (BVH) {
+        const float4 g = __ldg(bvh.geom + idx), cm = __ldg(bvh.color + idx);
+        ctr = make_float4(g.x, g.y, g.z, cm.w);
+        col = cm;
+        emi = __ldg(bvh.emission + idx);
+    } else {
+        ctr = sh.center[idx];
+        col = sh.color[idx];
+        emi = sh.emission[idx];
+    }
     const float xx = __fadd_rn(p.ox, __fmul_rn(p.dx, tmin)), xy = __fadd_rn(p.oy, __fmul_rn(p.dy, tmin)), xz = __fadd_rn(p.oz, __fmul_rn(p.dz, tmin));
     float nx = __fsub_rn(xx, ctr.x), ny = __fsub_rn(xy, ctr.y), nz = __fsub_rn(xz, ctr.z);
     normalize_rn(nx, ny, nz);

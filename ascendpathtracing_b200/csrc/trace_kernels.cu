@@ -169,14 +169,19 @@ __global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const Tra
 
 // ---- material extension kernel (pt_material.cuh) ------------------------------------------------------------------
 // Same persistent warps, ring and ballot-ranked regeneration; one iteration = one bounce of material_bounce().
-template <int NS>
+template <int NS, bool BVH>
 __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                            int max_depth, int rr_start, int nsph, int stride, float eps, float one,
                                                                            unsigned long long seed, unsigned long long path0,
-                                                                           unsigned long long *__restrict__ stats) {
+                                                                           unsigned long long *__restrict__ stats, const BvhScene bvh) {
     extern __shared__ float4 smem[];
     MatShared sh;
-    stage_materials_shared(smem, spheres, nsph, stride, sh);
+    if (BVH) {
+        sh.center = sh.color = sh.emission = nullptr;  // per-sphere data comes from global memory
+        __syncthreads();
+    } else {
+        stage_materials_shared(smem, spheres, nsph, stride, sh);
+    }
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
     const unsigned int warp = blockIdx.x * kWarpsPerBlock + warp_in_block;
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
     const unsigned long long wb = static_cast<unsigned long long>(warp) * per;
     const unsigned int wbeg = wb < count ? static_cast<unsigned int>(wb) : count;
     const unsigned int wcount = (count - wbeg) < per ? (count - wbeg) : per;
-    float *ring = reinterpret_cast<float *>(smem + 3 * nsph) + warp_in_block * (6 * kRing);
+    float *ring = reinterpret_cast<float *>(smem + (BVH ? 0 : 3 * nsph)) + warp_in_block * (6 * kRing);
 
     auto issue_batch = [&](unsigned int b) {
         const unsigned int e = b * 32u + lane;
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
         }
         if (active) {  // dead lanes of a finished range idle; live ones diverge by material inside
             segs++;
-            const bool ended = material_bounce<NS>(p, nsph, one, eps, rr_start, seed, path0 + wbeg + mine, sh);
+            const bool ended = material_bounce<NS, BVH>(p, nsph, one, eps, rr_start, seed, path0 + wbeg + mine, sh, bvh);
             want = ended || p.depth >= max_depth;
         }
     }
@@ -381,10 +386,20 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
 }
 
 
-cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMaterialParams &mp, const float *rays, const float *spheres,
-                            float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats) {
+cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtMaterialParams &mp, const float *rays, const float *spheres_in,
+                            float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats, const PtBvh *tree) {
     if (count <= 0)
         return cudaSuccess;
+    // With a tree, the constant bank and the kernel's brute-force loop see only the huge spheres (compacted SoA, stride 1024).
+    PtParams p = p_in;
+    const float *spheres = spheres_in;
+    BvhScene bvh = {};
+    if (tree != nullptr) {
+        bvh = bvh_scene(tree);
+        spheres = bvh_big_soa(tree);
+        p.sphere_count = bvh_big_count(tree);
+        p.sphere_stride = 1024;
+    }
     std::lock_guard<std::mutex> lock(g_mu);
     DeviceState *s = nullptr;
     cudaError_t e = ensure_device_state(&s);
@@ -394,14 +409,18 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMate
         if ((e = cudaStreamWaitEvent(stream, s->scene_free, 0)) != cudaSuccess)
             return e;
     }
-    pack_scene_kernel<<<1, 128, 0, stream>>>(spheres, p.sphere_count, p.sphere_stride, s->scene_alias, s->zero_ok_alias);
-    if ((e = cudaGetLastError()) != cudaSuccess)
-        return e;
-    const size_t smem = sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
-    const bool ten = p.sphere_count == 9 || p.sphere_count == 10;  // smallpt's scene: fully unrolled pairs (index 9 is padding)
+    if (p.sphere_count > 0) {
+        pack_scene_kernel<<<1, 128, 0, stream>>>(spheres, p.sphere_count, p.sphere_stride, s->scene_alias, s->zero_ok_alias);
+        if ((e = cudaGetLastError()) != cudaSuccess)
+            return e;
+    }
+    const bool use_tree = tree != nullptr;
+    const size_t smem = (use_tree ? 0 : sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count)) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
+    const bool ten = !use_tree && (p.sphere_count == 9 || p.sphere_count == 10);  // smallpt's scene: unrolled pairs (index 9 is padding)
     int occ = 0;
-    if ((e = ten ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<10>, kTraceThreads, smem)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0>, kTraceThreads, smem)) != cudaSuccess)
+    if ((e = use_tree ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, true>, kTraceThreads, smem)
+              : ten   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<10, false>, kTraceThreads, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, false>, kTraceThreads, smem)) != cudaSuccess)
         return e;
     if (occ < 1)
         occ = 1;
@@ -416,14 +435,17 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMate
             pl.col[c] = colors + c * n + a;
         const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
         const int grid = static_cast<int>(need < cap ? need : cap);
-        if (ten)
-            trace_materials_kernel<10><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), mp.max_depth, mp.rr_start,
-                                                                              p.sphere_count, p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed,
-                                                                              path0 + static_cast<uint64_t>(a - first), stats);
+        const unsigned int mm = static_cast<unsigned int>(m);
+        const unsigned long long pp = path0 + static_cast<uint64_t>(a - first);
+        if (use_tree)
+            trace_materials_kernel<0, true><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
+                                                                                   p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh);
+        else if (ten)
+            trace_materials_kernel<10, false><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
+                                                                                     p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh);
         else
-            trace_materials_kernel<0><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), mp.max_depth, mp.rr_start,
-                                                                             p.sphere_count, p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed,
-                                                                             path0 + static_cast<uint64_t>(a - first), stats);
+            trace_materials_kernel<0, false><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
+                                                                                    p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh);
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }

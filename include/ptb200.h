@@ -160,6 +160,29 @@ PTB200_API int ptb200_smallpt_scene(float *out176_host);
 PTB200_API int ptb200_render_image_mat(const PtParams *p, const PtMaterialParams *mp, void *stream, const uint8_t *spheres, uint64_t cam_seed,
                             int32_t x0, int32_t x1, int32_t gamma, uint8_t *image, uint64_t *stats);
 
+/* ---- large scenes: GPU-built sphere BVH (BASELINE config C4; NOT in the reference) ------- */
+
+typedef struct PtBvh PtBvh;
+/* Builds an LBVH (Morton order, Karras hierarchy) over the spheres of an 11-row SoA [11][stride] on the device.
+ * Spheres of radius >= 100 (the 1e5-radius walls, the light) stay in a brute-force list; the tree's boxes are padded so
+ * that the nearest hit equals the brute-force loop's bit for bit (t, index, lowest index on ties) for rays that start
+ * inside the scene.  Synchronous; the handle owns its device memory and keeps no reference to `spheres`. */
+PTB200_API int ptb200_bvh_build(const uint8_t *spheres, int32_t count, int32_t stride, void *stream, PtBvh **out);
+PTB200_API int ptb200_bvh_destroy(PtBvh *bvh);
+PTB200_API int ptb200_bvh_info(const PtBvh *bvh, int32_t *n_spheres, int32_t *n_big, int32_t *n_small, int32_t *n_nodes);
+/* Nearest hit only (the stage the tree replaces): rays SoA [6][n] -> tmin[n], index[n]; (1e20, 0) when nothing is hit. */
+PTB200_API int ptb200_bvh_first_hit(const PtBvh *bvh, void *stream, const float *rays, int64_t n, float eps, float *tmin_out, int32_t *idx_out);
+/* render_do_mat / ptb200_render_image_mat with the scene taken from the tree (p->sphere_count / sphere_stride are ignored). */
+PTB200_API int render_do_mat_bvh(const PtParams *p, const PtMaterialParams *mp, const PtBvh *bvh, void *stream, const uint8_t *rays, uint8_t *colors,
+                      int64_t first, int64_t count, uint64_t path0, uint64_t *stats);
+PTB200_API int ptb200_render_image_mat_bvh(const PtParams *p, const PtMaterialParams *mp, const PtBvh *bvh, void *stream, uint64_t cam_seed, int32_t x0,
+                                int32_t x1, int32_t gamma, uint8_t *image, uint64_t *stats);
+/* HOST helper: the synthetic scene of BASELINE config C4: the reference's six walls and light
+ * (scripts/gen_data.py:94-102, walls DIFF) followed by n_random spheres with centres uniform in [1,99]x[0,81.6]x[0,170],
+ * radius uniform in [0.2,1], material uniform in {DIFF,SPEC,REFR}, colour uniform in [0.2,0.95]^3, drawn in that order
+ * from NumPy-legacy MT19937(seed) doubles.  out: float32 SoA [11][stride], stride >= 7 + n_random. */
+PTB200_API int ptb200_random_scene(int32_t n_random, uint32_t seed, int32_t stride, float *out_host);
+
 /* ---- whole-job host-buffer entry (what the reference's main() does, src/main.cpp:46-92) --------- */
 
 /* HOST buffers in, HOST buffer out: arena allocation, H2D of rays+spheres, render, D2H of colours,

@@ -28,7 +28,7 @@ def lib():
         L.pto_trace.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_int, ctypes.c_int, ctypes.c_float]
         L.pto_first_hit.restype = None
-        L.pto_first_hit.argtypes = [_f32p, _f32p, _f32p, _i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+        L.pto_first_hit.argtypes = [_f32p, _f32p, _f32p, _i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_float]
         L.pto_mt_words.restype = None
         L.pto_mt_words.argtypes = [ctypes.c_uint32, _u32p, ctypes.c_int64]
         L.pto_mt_doubles.restype = None
@@ -56,6 +56,8 @@ def lib():
         L.pm_trace_f64.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64]
         L.pm_sincos2pi_array.restype = None
         L.pm_sincos2pi_array.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int64]
+        L.pm_random_scene.restype = None
+        L.pm_random_scene.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_int, _f32p]
         L.pm_smallpt_scene.restype = None
         L.pm_smallpt_scene.argtypes = [_f32p]
         L.pto_write_ppm.restype = ctypes.c_int
@@ -80,13 +82,13 @@ def trace(rays, spheres, depth=5, nsph=8, stride=None, light=7, scale=12.0, firs
     return (colors, int(live)) if return_live else colors
 
 
-def first_hit(rays, spheres, nsph=8, stride=None):
+def first_hit(rays, spheres, nsph=8, stride=None, eps=1e-4):
     rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(6, -1)
     n = rays.shape[1]
     spheres = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1)
     t = np.zeros(n, dtype=np.float32)
     idx = np.zeros(n, dtype=np.int32)
-    lib().pto_first_hit(rays.reshape(-1), spheres, t, idx, n, nsph, nsph if stride is None else stride)
+    lib().pto_first_hit(rays.reshape(-1), spheres, t, idx, n, nsph, nsph if stride is None else stride, eps)
     return t, idx
 
 
@@ -158,6 +160,13 @@ def mean_f32(a):
 def smallpt_scene():
     out = np.zeros(176, dtype=np.float32)
     lib().pm_smallpt_scene(out)
+    return out
+
+
+def random_scene(n_random, seed=12345, stride=None):
+    stride = 7 + n_random if stride is None else stride
+    out = np.zeros(11 * stride, dtype=np.float32)
+    lib().pm_random_scene(n_random, seed, stride, out)
     return out
 
 

@@ -138,7 +138,7 @@ uint64_t pto_trace(const float *rays, const float *spheres, float *colors, int64
 }
 
 /* First-hit only (stage check): writes tmin and idx of bounce 0 for each path. */
-void pto_first_hit(const float *rays, const float *spheres, float *tmin_out, int32_t *idx_out, int64_t n, int nsph, int stride) {
+void pto_first_hit(const float *rays, const float *spheres, float *tmin_out, int32_t *idx_out, int64_t n, int nsph, int stride, float eps) {
     const float *R2 = spheres, *CX = spheres + stride, *CY = spheres + 2 * stride, *CZ = spheres + 3 * stride;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; i++) {
@@ -160,8 +160,8 @@ void pto_first_hit(const float *rays, const float *spheres, float *tmin_out, int
             disc = disc - c;
             float s = sqrtf(disc);
             float t0 = b - s, t1 = b + s;
-            float t = (t0 > PTO_EPS) ? t0 : t1;
-            t = (t > PTO_EPS) ? t : PTO_MISS;
+            float t = (t0 > eps) ? t0 : t1;
+            t = (t > eps) ? t : PTO_MISS;
             if (k == 0 || t < tmin) {
                 tmin = t;
                 idx = k;

@@ -257,6 +257,35 @@ void pm_smallpt_scene(float *out176) {
             out176[m * 16 + i] = (float)(m == 0 ? tbl[i][m] * tbl[i][m] : tbl[i][m]);
 }
 
+/* BASELINE config C4 scene (inputs C4): reference walls + light, then n_random spheres from NumPy-legacy
+ * MT19937(seed) doubles in the order cx, cy, cz, radius, material, cr, cg, cb.  SoA [11][stride]. */
+void pto_mt_doubles(uint32_t seed, int64_t skip, double *out, int64_t n); /* pt_oracle.c */
+void pm_random_scene(int n_random, uint32_t seed, int stride, float *out) {
+    static const double base[7][11] = {
+        {1e5, 1e5 + 1, 40.8, 81.6, 0, 0, 0, 0.435, 0.376, 0.667, 0},  {1e5, -1e5 + 99, 40.8, 81.6, 0, 0, 0, 0.667, 0.129, 0.086, 0},
+        {1e5, 50, 40.8, 1e5, 0, 0, 0, 0.270, 0.725, 0.486, 0},        {1e5, 50, 40.8, -1e5 + 170, 0, 0, 0, 0, 0, 0, 0},
+        {1e5, 50, 1e5, 81.6, 0, 0, 0, 0.5, 0.5, 0.5, 0},              {1e5, 50, -1e5 + 81.6, 81.6, 0, 0, 0, 0.141, 0.408, 0.635, 0},
+        {600, 50, 681.6 - 0.27, 81.6, 12, 12, 12, 0, 0, 0, 0}};
+    memset(out, 0, sizeof(float) * 11 * (size_t)stride);
+    for (int i = 0; i < 7; i++)
+        for (int m = 0; m < 11; m++)
+            out[(size_t)m * stride + i] = (float)(m == 0 ? base[i][m] * base[i][m] : base[i][m]);
+    double *u = (double *)malloc(sizeof(double) * 8 * (size_t)(n_random > 0 ? n_random : 1));
+    pto_mt_doubles(seed, 0, u, 8 * (int64_t)n_random);
+    for (int k = 0; k < n_random; k++) {
+        const double *q = u + 8 * (size_t)k;
+        int i = 7 + k;
+        double r = 0.2 + 0.8 * q[3];
+        int mat = (int)(3.0 * q[4]);
+        if (mat > 2)
+            mat = 2;
+        double v[11] = {r * r, 1.0 + 98.0 * q[0], 81.6 * q[1], 170.0 * q[2], 0, 0, 0, 0.2 + 0.75 * q[5], 0.2 + 0.75 * q[6], 0.2 + 0.75 * q[7], (double)mat};
+        for (int m = 0; m < 11; m++)
+            out[(size_t)m * stride + i] = (float)v[m];
+    }
+    free(u);
+}
+
 /* ---- independent binary64 formulation (libm sin/cos, textbook order) for the statistical check ------------------- */
 static double rnd01(uint64_t *st) { /* splitmix64: an unrelated generator on purpose */
     uint64_t z = (*st += 0x9e3779b97f4a7c15ull);
