@@ -11,6 +11,8 @@
 // The scene lives in the constant bank (immediate operands) plus a shared copy for per-lane lookups.
 #include <cuda_pipeline.h>
 
+#include <cstdlib>
+
 #include "pt_device.cuh"
 #include "pt_host.h"
 #include "pt_material.cuh"
@@ -60,44 +62,90 @@ constexpr int kRingBatches = 4;                  // batches of 32 rays in the ri
 constexpr int kRing = 32 * kRingBatches;         // ring entries per warp
 constexpr int kWarpsPerBlock = kTraceThreads / 32;
 
+constexpr int kChunkBatches = 64;  // a warp claims 64 batches = 2048 consecutive paths at a time
+
+// Streams paths to one warp: chunks of 2048 consecutive paths are claimed from a global counter (dynamic balancing:
+// with a static split the slowest warp set the kernel's duration and a third of the warp slots sat idle at the end),
+// fetched by coalesced cp.async batches of 32 rays into a shared-memory ring kRingBatches batches ahead of use, and
+// handed to the lanes that ask for a path in ballot-rank order, i.e. consecutive indices to the lanes of one swap.
+struct PathFeeder {
+    const TracePlanes &pl;
+    float *ring;
+    unsigned long long *counter;
+    unsigned int count, lane;
+    unsigned int chunk_even, chunk_odd;  // first path of the chunk with even / odd sequence number (>= count: no such chunk)
+    unsigned int issued, head;
+
+    __device__ __forceinline__ PathFeeder(const TracePlanes &planes, float *ring_, unsigned long long *counter_, unsigned int count_, unsigned int lane_)
+        : pl(planes), ring(ring_), counter(counter_), count(count_), lane(lane_), issued(0), head(0) {
+        chunk_even = chunk_odd = count_;
+        for (int b = 0; b < kRingBatches; b++)
+            issue();
+    }
+    __device__ __forceinline__ unsigned int path_of(unsigned int seq) const {  // warp-local sequence number -> path index
+        const unsigned int batch = seq >> 5;
+        return (((batch / kChunkBatches) & 1u) ? chunk_odd : chunk_even) + (batch % kChunkBatches) * 32u + (seq & 31u);
+    }
+    __device__ __forceinline__ void issue() {  // warp-uniform: every lane commits a (possibly empty) group
+        if (issued % kChunkBatches == 0) {
+            unsigned long long base = 0;
+            if (lane == 0)
+                base = atomicAdd(counter, static_cast<unsigned long long>(32 * kChunkBatches));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned int first = base < count ? static_cast<unsigned int>(base) : count;
+            if ((issued / kChunkBatches) & 1u)
+                chunk_odd = first;
+            else
+                chunk_even = first;
+        }
+        const unsigned int seq = issued * 32u + lane;
+        const unsigned int path = path_of(seq);
+        if (path < count) {
+            const unsigned int s = seq & (kRing - 1);
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+                __pipeline_memcpy_async(ring + c * kRing + s, pl.ray[c] + path, sizeof(float));
+        }
+        __pipeline_commit();
+        issued++;
+    }
+    // Called by the whole warp when at least one lane wants a path.  Returns true and the ray for lanes that got one.
+    __device__ __forceinline__ bool take(bool want, unsigned int wmask, unsigned int &path, float (&ray)[6]) {
+        const unsigned int seq = head + __popc(wmask & ((1u << lane) - 1u));
+        path = path_of(seq);
+        const bool got = want && path < count;
+        __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
+        __syncwarp();              // ... and is visible to the other lanes of the warp
+        if (got) {
+            const unsigned int s = seq & (kRing - 1);
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+                ray[c] = ring[c * kRing + s];
+        }
+        head += __popc(wmask);
+        __syncwarp();  // ring reads done before a slot can be refilled
+        if (issued < head / 32u + kRingBatches)
+            issue();
+        return got;
+    }
+};
+
 template <int NS, bool EARLY>
 __global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
-                                                                    int depth, int nsph, int stride, int light, float scale, float one,
-                                                                    unsigned long long *__restrict__ stats) {
+                                                                       int depth, int nsph, int stride, int light, float scale, float one,
+                                                                       unsigned long long *__restrict__ stats, unsigned long long *work_counter) {
     extern __shared__ float4 smem[];
     SceneShared sh;
     stage_scene_shared(smem, spheres, nsph, stride, sh);
     const bool zero_stop = c_scene_zero_stop_ok != 0;
 
-    // Persistent warps with path regeneration.  Each warp owns a contiguous range of paths and hands them
-    // out in order: lanes whose path finished in this iteration are ranked by a ballot and take the next
-    // consecutive indices, so the rays they fetch and (to within the few paths in flight) the colours they
-    // store share cache lines even though the lanes are at different bounces of different paths.
-    // The range is streamed through a per-warp shared-memory ring, four coalesced cp.async batches of 32
-    // rays ahead of consumption, so a swap costs six LDS instead of an exposed HBM round trip.
+    // Persistent warps with path regeneration.  The loop body is exactly one bounce, so the lanes of a warp may be at
+    // different bounces of different paths without diverging.  Lanes whose path finished are ranked by a ballot and take
+    // the next consecutive paths of the warp's current chunk, so the rays they fetch and (to within the few paths in
+    // flight) the colours they store share cache lines.  See PathFeeder for how paths reach the warp.
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    const unsigned int warp = blockIdx.x * kWarpsPerBlock + warp_in_block;
-    const unsigned int nwarps = gridDim.x * kWarpsPerBlock;
-    const unsigned int per = ((count + nwarps - 1) / nwarps + 31u) & ~31u;
-    const unsigned long long wb = static_cast<unsigned long long>(warp) * per;
-    const unsigned int wbeg = wb < count ? static_cast<unsigned int>(wb) : count;
-    const unsigned int wcount = (count - wbeg) < per ? (count - wbeg) : per;  // paths of this warp
-    float *ring = reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * (6 * kRing);
-
-    auto issue_batch = [&](unsigned int b) {  // warp-uniform: every lane commits a (possibly empty) group
-        const unsigned int e = b * 32u + lane;
-        if (e < wcount) {
-            const unsigned int s = e & (kRing - 1);
-#pragma unroll
-            for (int c = 0; c < 6; c++)
-                __pipeline_memcpy_async(ring + c * kRing + s, pl.ray[c] + wbeg + e, sizeof(float));
-        }
-        __pipeline_commit();
-    };
-    unsigned int issued = 0;
-    for (; issued < kRingBatches; issued++)
-        issue_batch(issued);
+    PathFeeder feed(pl, reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
 
     PathState p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -106,8 +154,7 @@ __global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const Tra
     p.alive = true;
     int bounce = 0;
     unsigned int segs = 0;
-    unsigned int head = 0;      // next unassigned path of the warp's range (warp-uniform)
-    unsigned int mine = 0;      // offset of the path this lane holds
+    unsigned int mine = 0;      // path this lane holds
     bool active = false;        // this lane holds a real path
     bool want = true;           // this lane needs a (new) path
 
@@ -115,36 +162,24 @@ __global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const Tra
         const unsigned int wmask = __ballot_sync(0xffffffffu, want);
         if (wmask != 0u) {  // warp-uniform
             if (active && want) {  // lanes that finished a path in the previous iteration
-                const unsigned int i = wbeg + mine;
-                pl.col[0][i] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
-                pl.col[1][i] = __fmul_rn(p.rg, scale);
-                pl.col[2][i] = __fmul_rn(p.rb, scale);
+                pl.col[0][mine] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
+                pl.col[1][mine] = __fmul_rn(p.rg, scale);
+                pl.col[2][mine] = __fmul_rn(p.rb, scale);
                 segs += bounce;
             }
-            const unsigned int rank = __popc(wmask & ((1u << lane) - 1u));
-            const unsigned int e = head + rank;
-            const bool take = want && e < wcount;
-            __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
-            __syncwarp();              // ... and is visible to the other lanes of the warp
-            if (take) {
-                const unsigned int s = e & (kRing - 1);
-                p.ox = ring[0 * kRing + s], p.oy = ring[1 * kRing + s], p.oz = ring[2 * kRing + s];
-                p.dx = ring[3 * kRing + s], p.dy = ring[4 * kRing + s], p.dz = ring[5 * kRing + s];
-                mine = e;
+            unsigned int path;
+            float ray[6];
+            const bool got = feed.take(want, wmask, path, ray);
+            if (got) {
+                p.ox = ray[0], p.oy = ray[1], p.oz = ray[2], p.dx = ray[3], p.dy = ray[4], p.dz = ray[5];
+                mine = path;
             }
             if (want) {
-                active = take;
+                active = got;
                 p.rr = p.rg = p.rb = 1.0f;
                 p.alive = true;
                 bounce = 0;
                 want = false;
-            }
-            head += __popc(wmask);
-            head = head < wcount ? head : wcount;
-            __syncwarp();  // ring reads done before a slot can be refilled
-            if (issued < head / 32u + kRingBatches) {
-                issue_batch(issued);
-                issued++;
             }
             if (!__any_sync(0xffffffffu, active))
                 break;
@@ -173,7 +208,8 @@ template <int NS, bool BVH>
 __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                            int max_depth, int rr_start, int nsph, int stride, float eps, float one,
                                                                            unsigned long long seed, unsigned long long path0,
-                                                                           unsigned long long *__restrict__ stats, const BvhScene bvh) {
+                                                                           unsigned long long *__restrict__ stats, const BvhScene bvh,
+                                                                           unsigned long long *work_counter) {
     extern __shared__ float4 smem[];
     MatShared sh;
     if (BVH) {
@@ -184,27 +220,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
     }
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    const unsigned int warp = blockIdx.x * kWarpsPerBlock + warp_in_block;
-    const unsigned int nwarps = gridDim.x * kWarpsPerBlock;
-    const unsigned int per = ((count + nwarps - 1) / nwarps + 31u) & ~31u;
-    const unsigned long long wb = static_cast<unsigned long long>(warp) * per;
-    const unsigned int wbeg = wb < count ? static_cast<unsigned int>(wb) : count;
-    const unsigned int wcount = (count - wbeg) < per ? (count - wbeg) : per;
-    float *ring = reinterpret_cast<float *>(smem + (BVH ? 0 : 3 * nsph)) + warp_in_block * (6 * kRing);
-
-    auto issue_batch = [&](unsigned int b) {
-        const unsigned int e = b * 32u + lane;
-        if (e < wcount) {
-            const unsigned int s = e & (kRing - 1);
-#pragma unroll
-            for (int c = 0; c < 6; c++)
-                __pipeline_memcpy_async(ring + c * kRing + s, pl.ray[c] + wbeg + e, sizeof(float));
-        }
-        __pipeline_commit();
-    };
-    unsigned int issued = 0;
-    for (; issued < kRingBatches; issued++)
-        issue_batch(issued);
+    PathFeeder feed(pl, reinterpret_cast<float *>(smem + (BVH ? 0 : 3 * nsph)) + warp_in_block * (6 * kRing), work_counter, count, lane);
 
     MatPath p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -212,49 +228,37 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
     p.tr = p.tg = p.tb = 1.0f;
     p.lr = p.lg = p.lb = 0.0f;
     p.depth = 0;
-    unsigned int segs = 0, head = 0, mine = 0;
+    unsigned int segs = 0, mine = 0;
     bool active = false, want = true;
 
     for (;;) {
         const unsigned int wmask = __ballot_sync(0xffffffffu, want);
         if (wmask != 0u) {
             if (active && want) {
-                const unsigned int i = wbeg + mine;
-                pl.col[0][i] = p.lr;
-                pl.col[1][i] = p.lg;
-                pl.col[2][i] = p.lb;
+                pl.col[0][mine] = p.lr;
+                pl.col[1][mine] = p.lg;
+                pl.col[2][mine] = p.lb;
             }
-            const unsigned int rank = __popc(wmask & ((1u << lane) - 1u));
-            const unsigned int e = head + rank;
-            const bool take = want && e < wcount;
-            __pipeline_wait_prior(1);
-            __syncwarp();
-            if (take) {
-                const unsigned int s = e & (kRing - 1);
-                p.ox = ring[0 * kRing + s], p.oy = ring[1 * kRing + s], p.oz = ring[2 * kRing + s];
-                p.dx = ring[3 * kRing + s], p.dy = ring[4 * kRing + s], p.dz = ring[5 * kRing + s];
-                mine = e;
+            unsigned int path;
+            float ray[6];
+            const bool got = feed.take(want, wmask, path, ray);
+            if (got) {
+                p.ox = ray[0], p.oy = ray[1], p.oz = ray[2], p.dx = ray[3], p.dy = ray[4], p.dz = ray[5];
+                mine = path;
             }
             if (want) {
-                active = take;
+                active = got;
                 p.tr = p.tg = p.tb = 1.0f;
                 p.lr = p.lg = p.lb = 0.0f;
                 p.depth = 0;
                 want = false;
-            }
-            head += __popc(wmask);
-            head = head < wcount ? head : wcount;
-            __syncwarp();
-            if (issued < head / 32u + kRingBatches) {
-                issue_batch(issued);
-                issued++;
             }
             if (!__any_sync(0xffffffffu, active))
                 break;
         }
         if (active) {  // dead lanes of a finished range idle; live ones diverge by material inside
             segs++;
-            const bool ended = material_bounce<NS, BVH>(p, nsph, one, eps, rr_start, seed, path0 + wbeg + mine, sh, bvh);
+            const bool ended = material_bounce<NS, BVH>(p, nsph, one, eps, rr_start, seed, path0 + mine, sh, bvh);
             want = ended || p.depth >= max_depth;
         }
     }
@@ -277,6 +281,7 @@ struct DeviceState {
     int blocks_per_sm[4] = {0, 0, 0, 0};  // [NS8?][EARLY?]
     SceneConst *scene_alias = nullptr;
     int *zero_ok_alias = nullptr;
+    unsigned long long *work_counter = nullptr;  // chunk dispenser of the persistent kernels (reset before every launch)
     cudaEvent_t scene_free = nullptr;  // recorded after the last kernel that reads the staged scene
     cudaStream_t last_stream = nullptr;
     bool have_last = false;
@@ -307,6 +312,8 @@ cudaError_t ensure_device_state(DeviceState **out) {
             return e;
         if ((e = cudaEventCreateWithFlags(&s.scene_free, cudaEventDisableTiming)) != cudaSuccess)
             return e;
+        if ((e = cudaMalloc(reinterpret_cast<void **>(&s.work_counter), sizeof(unsigned long long))) != cudaSuccess)
+            return e;
         s.init = true;
     }
     *out = &s;
@@ -336,9 +343,13 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
             pl.col[c] = colors + c * n + a;
         const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
         const int grid = static_cast<int>(need < cap ? need : cap);
+        cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess)
+            return e;
         trace_paths_kernel<NS, EARLY><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), p.depth, p.sphere_count,
-                                                                             p.sphere_stride, p.light_index, p.emission_scale, 1.0f, stats);
-        cudaError_t e = cudaGetLastError();
+                                                                             p.sphere_stride, p.light_index, p.emission_scale, 1.0f, stats,
+                                                                             s.work_counter);
+        e = cudaGetLastError();
         if (e != cudaSuccess)
             return e;
     }
@@ -366,10 +377,15 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
     if ((e = cudaGetLastError()) != cudaSuccess)
         return e;
     // Early termination and the fixed-depth loop give identical bits, so which one runs is a pure performance choice:
-    // lock-step lanes swap paths once per `depth` iterations, regenerating lanes once per iteration.  Measured on B200
-    // (profiles/r1_depth_sweep.md): fixed wins up to depth ~7 (5.85 vs 6.27 ms at depth 5), regeneration beyond
-    // (30.7 vs 133.6 ms at depth 50).
-    const bool early = !(p.flags & PTB200_F_FIXED_DEPTH) && p.depth > 7;
+    // lock-step lanes swap paths once per `depth` iterations (115 Gsegments/s), regenerating lanes every iteration
+    // (95-99 Gsegments/s) but they skip the settled part of every path: 22 % of the segments at depth 5, 13 % at depth 4.
+    // Measured on B200 (profiles/r1_depth_sweep.md): regeneration wins from depth 5 on (5.49 vs 5.77 ms at depth 5,
+    // 20.4 vs 107 ms at depth 50).
+    static const int min_early_depth = [] {  // PTB200_EARLY_FROM_DEPTH overrides the crossover (experiments)
+        const char *e = getenv("PTB200_EARLY_FROM_DEPTH");
+        return e ? atoi(e) : 5;
+    }();
+    const bool early = !(p.flags & PTB200_F_FIXED_DEPTH) && p.depth >= min_early_depth;
     if (p.sphere_count == 8)
         e = early ? launch_trace<8, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats)
                   : launch_trace<8, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats);
@@ -435,17 +451,22 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
             pl.col[c] = colors + c * n + a;
         const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
         const int grid = static_cast<int>(need < cap ? need : cap);
+        if ((e = cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned long long), stream)) != cudaSuccess)
+            return e;
         const unsigned int mm = static_cast<unsigned int>(m);
         const unsigned long long pp = path0 + static_cast<uint64_t>(a - first);
         if (use_tree)
             trace_materials_kernel<0, true><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
-                                                                                   p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh);
+                                                                                   p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh,
+                                                                                   s->work_counter);
         else if (ten)
             trace_materials_kernel<10, false><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
-                                                                                     p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh);
+                                                                                     p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh,
+                                                                                   s->work_counter);
         else
             trace_materials_kernel<0, false><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
-                                                                                    p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh);
+                                                                                    p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh,
+                                                                                   s->work_counter);
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }

@@ -299,7 +299,7 @@ def main():
         peak_tflops = 2.0 * ffma_gops / 1e3
         achieved = FLOPS_PER_PATH * n / (trace_ms * 1e-3) / 1e12
         hbm_peak = pk.get("hbm_gbs")
-        roofline = {"bound": "fp32", "kernel": "trace_paths_kernel<8,true>", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+        roofline = {"bound": "fp32", "kernel": "trace_paths_kernel<8,true> (persistent warps, regeneration, exact early termination)", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                     "frac": achieved / peak_tflops, "traffic": None,
                     "peak_source": "measured live: dependent-free FFMA micro-kernel (ptb200_measure_fp32 kind 0), 2 FLOP per FFMA",
                     "kernel_ms": trace_ms, "algorithmic_flops_per_path": FLOPS_PER_PATH,

@@ -261,9 +261,9 @@ def test_render_image_counter_rng_and_stats(pt, cuda, oracle):
     w, h, s, seed = 40, 24, 4, 99
     d_sph = dev(torch, pt.default_scene())
     d_stats = torch.zeros(2, dtype=torch.int64, device="cuda")
-    # depth 10: regeneration with exact early termination -> segments traced == the oracle's count of live segments;
-    # depth 5: the library runs the (bit-identical) lock-step loop because it is faster there -> every segment is traced
-    for depth in (10, 5):
+    # depth >= 5: regeneration with exact early termination -> segments traced == the oracle's count of live segments;
+    # below, the library runs the (bit-identical) lock-step loop because it is faster there -> every segment is traced
+    for depth in (10, 5, 3):
         p = pt.default_params(width=w, height=h, samples=s, depth=depth)
         n = p.n_paths
         d_img = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
@@ -273,7 +273,7 @@ def test_render_image_counter_rng_and_stats(pt, cuda, oracle):
         assert np.array_equal(d_img.cpu().numpy(), oracle.resolve(col, w, h, s))
         stats = d_stats.cpu().numpy()
         assert stats[0] == n
-        assert stats[1] == (live if depth > 7 else n * depth)
+        assert stats[1] == (live if depth >= 5 else n * depth)
     # column stripes (the multi-GPU partition) tile the same image
     for x0, x1 in [(0, 7), (7, 25), (25, 40)]:
         d_part = torch.zeros((h, x1 - x0, 3), dtype=torch.uint8, device="cuda")
@@ -343,7 +343,7 @@ def test_c2_full_size_properties(pt, cuda, oracle):
     d_sph = dev(torch, pt.default_scene())
     d_a = torch.empty(3 * n, dtype=torch.float32, device="cuda")
     d_b = torch.empty(3 * n, dtype=torch.float32, device="cuda")
-    # (1) at depth 10, where the library regenerates paths with early termination unless told otherwise
+    # (1) at depth 10 (regeneration with early termination unless told otherwise), then at the reference's depth 5
     p.depth = 10
     pt.render_do_ex(p, d_rays, d_sph, d_a)
     p.flags = 1
@@ -356,6 +356,11 @@ def test_c2_full_size_properties(pt, cuda, oracle):
                           bits(oracle.trace(d_rays.view(6, n)[:, idx10].cpu().numpy(), oracle.gen_spheres(), depth=10)))
     p.depth = 5
     pt.render_do_ex(p, d_rays, d_sph, d_a)
+    p.flags = 1
+    pt.render_do_ex(p, d_rays, d_sph, d_b)
+    p.flags = 0
+    torch.cuda.synchronize()
+    assert torch.equal(d_a.view(torch.int32), d_b.view(torch.int32))
     idx = torch.arange(0, n, 503, device="cuda")
     rays_s = d_rays.view(6, n)[:, idx].cpu().numpy()
     got = d_a.view(3, n)[:, idx].cpu().numpy()
