@@ -59,7 +59,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("PTB200_LIB") or _build.build()  # PTB200_LIB: A/B-test another build of the same ABI
     L = ctypes.CDLL(path)
     c = ctypes
     vp, i32, i64, u32, u64, sz = c.c_void_p, c.c_int32, c.c_int64, c.c_uint32, c.c_uint64, c.c_size_t

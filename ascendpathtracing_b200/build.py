@@ -33,6 +33,13 @@ def nvcc():
     return "nvcc"
 
 
+def build_variant(name, defines):
+    """A/B builds for kernel experiments: libptb200_<name>.so with extra -D flags (select with PTB200_LIB=...)."""
+    out = os.path.join(HERE, f"libptb200_{name}.so")
+    subprocess.check_call([nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], *[os.path.join(CSRC, f) for f in SOURCES], "-o", out])
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB

@@ -20,7 +20,7 @@ namespace {
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).  Every step of a run reads one full 32-byte sector, and the kItems
 // independent streams keep enough loads in flight to run the colour planes through at HBM speed (a single
 // stream per warp is latency-bound at ~1 TB/s).
-constexpr int kPixPerWarp = 2;
+constexpr int kPixPerWarp = 4;
 constexpr int kItems = 3 * kPixPerWarp;  // pixels x channels resolved concurrently by one warp
 
 __device__ __forceinline__ void group_block_sum(const float *const (&a)[kItems], int64_t off, int n, int j, float (&r)[kItems]) {
@@ -104,51 +104,60 @@ __device__ void group_pairwise_sum(const float *const (&a)[kItems], int64_t n, i
 
 __global__ void __launch_bounds__(256) resolve_kernel(const float *__restrict__ colors, int64_t cn, int64_t pix0, int64_t npix, int h, int s,
                                                       uint8_t *__restrict__ image, int x_origin, int img_w, int gamma) {
-    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // warp = kPixPerWarp consecutive pixels
-    const int64_t q0 = w * kPixPerWarp;
-    if (q0 >= npix)
-        return;  // whole warp
     const int lane = threadIdx.x & 31;
     const int k = lane >> 3, j = lane & 7;  // sub-pixel run, accumulator
-    const float *run[kItems];
-    int64_t q[kItems];
+    const int64_t n_items = (npix + kPixPerWarp - 1) / kPixPerWarp;
+    const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    // grid-stride over warp items: a few thousand resident warps walk the frame (one block per 16 pixels would spend
+    // more time launching 400 k blocks than reading the 600 MB)
+    for (int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n_items; w += warps) {
+        const int64_t q0 = w * kPixPerWarp;
+        const float *run[kItems];
+        int64_t q[kItems];
 #pragma unroll
-    for (int u = 0; u < kItems; u++) {
-        const int64_t qq = q0 + u / 3;
-        q[u] = qq < npix ? qq : q0;  // a ragged tail recomputes pixel q0 (result discarded)
-        run[u] = colors + (u % 3) * cn + q[u] * 4 * s + static_cast<int64_t>(k) * s;
-    }
-    float m[kItems];
-    if (s == 1) {
+        for (int u = 0; u < kItems; u++) {
+            const int64_t qq = q0 + u / 3;
+            q[u] = qq < npix ? qq : q0;  // a ragged tail recomputes pixel q0 (result discarded)
+            run[u] = colors + (u % 3) * cn + q[u] * 4 * s + static_cast<int64_t>(k) * s;
+        }
+        float m[kItems];
+        if (s == 1) {
 #pragma unroll
-        for (int u = 0; u < kItems; u++)
-            m[u] = run[u][0];
-    } else {
-        group_pairwise_sum(run, s, j, m);
+            for (int u = 0; u < kItems; u++)
+                m[u] = run[u][0];
+        } else {
+            group_pairwise_sum(run, s, j, m);
 #pragma unroll
-        for (int u = 0; u < kItems; u++)
-            m[u] = __fdiv_rn(m[u], static_cast<float>(s));
-    }
+            for (int u = 0; u < kItems; u++)
+                m[u] = __fdiv_rn(m[u], static_cast<float>(s));
+        }
+        // The four sub-pixel means of item u live in lanes 0, 8, 16, 24.  Hand item u to lane u, then run the scalar
+        // epilogue ONCE with lanes 0..kItems-1 active (running it per item with one live lane made this kernel
+        // instruction-bound: 690 warp instructions per 1.5 KB).
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
 #pragma unroll
-    for (int u = 0; u < kItems; u++) {
-        // the four means live in lanes 0, 8, 16, 24; sum them in binary64 in sub-pixel order
-        const double m0 = static_cast<double>(__shfl_sync(0xffffffffu, m[u], 0));
-        const double m1 = static_cast<double>(__shfl_sync(0xffffffffu, m[u], 8));
-        const double m2 = static_cast<double>(__shfl_sync(0xffffffffu, m[u], 16));
-        const double m3 = static_cast<double>(__shfl_sync(0xffffffffu, m[u], 24));
-        if (lane != u || q0 + u / 3 >= npix)
-            continue;  // lane u writes item u
-        double v = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(m0, m1), m2), m3), 4.0);
-        v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
-        if (gamma)  // smallpt's display transform (material extension only; the reference has no gamma)
-            v = pow(v, 1.0 / 2.2) * 255.0 + 0.5;
-        else
-            v = __dmul_rn(v, 255.0);
-        const int64_t pix = pix0 + q[u];
-        const int x = static_cast<int>(pix / h);
-        const int y = static_cast<int>(pix - static_cast<int64_t>(x) * h);
-        const int row = h - 1 - y;
-        image[(static_cast<int64_t>(row) * img_w + (x - x_origin)) * 3 + (u % 3)] = static_cast<uint8_t>(static_cast<int>(v));
+        for (int u = 0; u < kItems; u++) {
+            const float a0 = __shfl_sync(0xffffffffu, m[u], 0), a1 = __shfl_sync(0xffffffffu, m[u], 8);
+            const float a2 = __shfl_sync(0xffffffffu, m[u], 16), a3 = __shfl_sync(0xffffffffu, m[u], 24);
+            if (lane == u)
+                m0 = a0, m1 = a1, m2 = a2, m3 = a3;
+        }
+        if (lane < kItems && q0 + lane / 3 < npix) {
+            // sum in binary64 in sub-pixel order (data_visualization.py:39-45)
+            double v = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(static_cast<double>(m0), static_cast<double>(m1)), static_cast<double>(m2)),
+                                           static_cast<double>(m3)),
+                                 4.0);
+            v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+            if (gamma)  // smallpt's display transform (material extension only; the reference has no gamma)
+                v = pow(v, 1.0 / 2.2) * 255.0 + 0.5;
+            else
+                v = __dmul_rn(v, 255.0);
+            const int64_t pix = pix0 + q0 + lane / 3;
+            const int x = static_cast<int>(pix / h);
+            const int y = static_cast<int>(pix - static_cast<int64_t>(x) * h);
+            const int row = h - 1 - y;
+            image[(static_cast<int64_t>(row) * img_w + (x - x_origin)) * 3 + (lane % 3)] = static_cast<uint8_t>(static_cast<int>(v));
+        }
     }
 }
 
@@ -158,7 +167,12 @@ cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *
                            uint8_t *image, int32_t x_origin, int32_t img_w, int gamma) {
     if (npix <= 0)
         return cudaSuccess;
-    const int64_t blocks = ((npix + kPixPerWarp - 1) / kPixPerWarp + 7) / 8;  // 8 warps per block
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t need = ((npix + kPixPerWarp - 1) / kPixPerWarp + 7) / 8;  // 8 warps per block
+    const int64_t cap = static_cast<int64_t>(sms) * 16;
+    const int64_t blocks = need < cap ? need : cap;
     resolve_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(colors, cn, pix0, npix, p.height, p.samples, image, x_origin, img_w, gamma);
     return cudaGetLastError();
 }

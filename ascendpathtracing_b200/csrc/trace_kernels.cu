@@ -109,29 +109,32 @@ struct PathFeeder {
         __pipeline_commit();
         issued++;
     }
-    // Called by the whole warp when at least one lane wants a path.  Returns true and the ray for lanes that got one.
-    __device__ __forceinline__ bool take(bool want, unsigned int wmask, unsigned int &path, float (&ray)[6]) {
-        const unsigned int seq = head + __popc(wmask & ((1u << lane) - 1u));
+    // Called by the whole warp when at least one lane wants a path.  Lanes that get one receive its index and a pointer
+    // to its ray in the ring (component c at slot[c * kRing]); the caller reads it and then calls refill().
+    __device__ __forceinline__ bool take(bool want, unsigned int wmask, unsigned int &path, const float *&slot) {
+        unsigned int lt;
+        asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+        const unsigned int seq = head + __popc(wmask & lt);
         path = path_of(seq);
         const bool got = want && path < count;
         __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
         __syncwarp();              // ... and is visible to the other lanes of the warp
-        if (got) {
-            const unsigned int s = seq & (kRing - 1);
-#pragma unroll
-            for (int c = 0; c < 6; c++)
-                ray[c] = ring[c * kRing + s];
-        }
+        slot = ring + (seq & (kRing - 1));
         head += __popc(wmask);
+        return got;
+    }
+    __device__ __forceinline__ void refill() {
         __syncwarp();  // ring reads done before a slot can be refilled
         if (issued < head / 32u + kRingBatches)
             issue();
-        return got;
     }
 };
 
+#ifndef PTB_BLOCKS_PER_SM
+#define PTB_BLOCKS_PER_SM 5
+#endif
 template <int NS, bool EARLY>
-__global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
+__global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                        int depth, int nsph, int stride, int light, float scale, float one,
                                                                        unsigned long long *__restrict__ stats, unsigned long long *work_counter) {
     extern __shared__ float4 smem[];
@@ -168,12 +171,14 @@ __global__ void __launch_bounds__(kTraceThreads, 5) trace_paths_kernel(const Tra
                 segs += bounce;
             }
             unsigned int path;
-            float ray[6];
-            const bool got = feed.take(want, wmask, path, ray);
+            const float *slot;
+            const bool got = feed.take(want, wmask, path, slot);
             if (got) {
-                p.ox = ray[0], p.oy = ray[1], p.oz = ray[2], p.dx = ray[3], p.dy = ray[4], p.dz = ray[5];
+                p.ox = slot[0 * kRing], p.oy = slot[1 * kRing], p.oz = slot[2 * kRing];
+                p.dx = slot[3 * kRing], p.dy = slot[4 * kRing], p.dz = slot[5 * kRing];
                 mine = path;
             }
+            feed.refill();
             if (want) {
                 active = got;
                 p.rr = p.rg = p.rb = 1.0f;
@@ -240,12 +245,14 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
                 pl.col[2][mine] = p.lb;
             }
             unsigned int path;
-            float ray[6];
-            const bool got = feed.take(want, wmask, path, ray);
+            const float *slot;
+            const bool got = feed.take(want, wmask, path, slot);
             if (got) {
-                p.ox = ray[0], p.oy = ray[1], p.oz = ray[2], p.dx = ray[3], p.dy = ray[4], p.dz = ray[5];
+                p.ox = slot[0 * kRing], p.oy = slot[1 * kRing], p.oz = slot[2 * kRing];
+                p.dx = slot[3 * kRing], p.dy = slot[4 * kRing], p.dz = slot[5 * kRing];
                 mine = path;
             }
+            feed.refill();
             if (want) {
                 active = got;
                 p.tr = p.tg = p.tb = 1.0f;
