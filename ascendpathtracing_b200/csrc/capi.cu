@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
 #include <string>
@@ -452,8 +453,13 @@ int ptb200_render_host(const PtParams *p, const float *rays_host, const float *s
     const size_t sph_alloc = sph_bytes < 512 ? 512 : sph_bytes;
     // Chunked so that the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap
     // (three engines, three streams).  With pinned host memory the copies are truly asynchronous.
-    constexpr int kStreams = 3;
-    int64_t chunk = 4LL << 20;  // paths per chunk: 96 MiB in, 48 MiB out
+    constexpr int kStreams = 4;
+    static const int64_t chunk_paths = [] {  // PTB200_HOST_CHUNK overrides (experiments)
+        const char *e = getenv("PTB200_HOST_CHUNK");
+        return e ? atoll(e) : (4LL << 20);
+    }();
+    int64_t chunk = chunk_paths;  // paths per chunk: 96 MiB in, 48 MiB out (measured: 1 Mi-path chunks are no faster, 256 Ki-path
+                                  // chunks halve the rate; the call is bound by PCIe at ~45 GB/s host-to-device)
     if (chunk > n)
         chunk = n;
     const int nbuf = static_cast<int>((n + chunk - 1) / chunk < kStreams ? (n + chunk - 1) / chunk : kStreams);
@@ -462,8 +468,8 @@ int ptb200_render_host(const PtParams *p, const float *rays_host, const float *s
     if ((rc = workspace(per_buf * nbuf + sph_alloc + 4096, &arena)) != PTB200_OK)
         return rc;
     float *d_sph = static_cast<float *>(ptb200_arena_alloc(arena, sph_alloc));
-    float *d_buf[kStreams] = {nullptr, nullptr, nullptr};
-    cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
+    float *d_buf[kStreams] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr, nullptr};
     cudaError_t e = cudaSuccess;
     bool ok = d_sph != nullptr;
     for (int b = 0; b < nbuf && ok; b++) {

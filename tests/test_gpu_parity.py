@@ -463,3 +463,22 @@ def test_c3_full_frame_spot_checks(pt, cuda, oracle):
             win[:, cx] = colimg[:, 0]
         got = img[h - 1 - (wy + 15):h - 1 - (wy + 15) + 16, wx - x0:wx - x0 + 16]
         assert np.array_equal(got, win), (wx, wy)
+
+
+def test_run_sh_gpu_mode_end_to_end(pt, cuda, golden_dir):
+    """`bash run.sh -r gpu` = the reference's run.sh flow (build, generate, run, visualise) on the B200 build; its
+    output/color.ppm and output/color.bin must be the files the reference's own pipeline produces for the default size."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        out = subprocess.run(["bash", os.path.join(root, "run.sh"), "-r", "gpu", "-v", "Ascend310P1"], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert "execute op on gpu succeed" in out.stdout
+        assert open(os.path.join(root, "output/color.ppm")).read() == open(os.path.join(golden_dir, "w16h16s1d5_color.ppm")).read()
+        assert open(os.path.join(root, "output/color.bin"), "rb").read() == open(os.path.join(golden_dir, "w16h16s1d5_color.bin"), "rb").read()
+        bad = subprocess.run(["bash", os.path.join(root, "run.sh"), "-r", "sim"], capture_output=True, text=True, timeout=60)
+        assert bad.returncode != 0
+    finally:
+        shutil.rmtree(os.path.join(root, "input"), ignore_errors=True)
+        shutil.rmtree(os.path.join(root, "output"), ignore_errors=True)
