@@ -299,8 +299,15 @@ def main():
         peak_tflops = 2.0 * ffma_gops / 1e3
         achieved = FLOPS_PER_PATH * n / (trace_ms * 1e-3) / 1e12
         hbm_peak = pk.get("hbm_gbs")
+        try:  # DRAM traffic and pipe utilisation of the same kernel from the committed ncu capture (profiles/)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_trace_ncu.json")))
+        except Exception:
+            prof = {}
         roofline = {"bound": "fp32", "kernel": "trace_paths_kernel<8,true> (persistent warps, regeneration, exact early termination)", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tflops, "traffic": None,
+                    "frac": achieved / peak_tflops, "traffic": prof.get("traffic_bytes_per_launch"),
+                    "traffic_algorithmic": BYTES_PER_PATH * n,
+                    "ncu": {k: prof.get(k) for k in ("fp32_pipe_active_pct", "alu_pipe_active_pct", "issue_active_pct", "branch_targets_uniform_pct",
+                                                     "achieved_warps_per_sm", "source")},
                     "peak_source": "measured live: dependent-free FFMA micro-kernel (ptb200_measure_fp32 kind 0), 2 FLOP per FFMA",
                     "kernel_ms": trace_ms, "algorithmic_flops_per_path": FLOPS_PER_PATH,
                     "exact_mode_ceiling": "every op is a singly rounded FADD/FMUL (no FFMA): at most 0.5 of the FFMA-FLOP peak",
