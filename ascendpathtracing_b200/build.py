@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptb200.so")
 SOURCES = ["capi.cu", "arena.cu", "trace_kernels.cu", "raygen_kernels.cu", "resolve_kernels.cu", "fp32_peak.cu", "bvh.cu"]
-HEADERS = ["pt_device.cuh", "pt_material.cuh", "pt_bvh.cuh", "pt_host.h", "philox.h", os.path.join("..", "..", "include", "ptb200.h")]
+HEADERS = ["pt_device.cuh", "pt_material.cuh", "pt_bvh.cuh", "pt_raygen.cuh", "pt_host.h", "philox.h", os.path.join("..", "..", "include", "ptb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

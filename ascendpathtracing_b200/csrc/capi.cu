@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "pt_host.h"
+#include "pt_raygen.cuh"
 
 namespace ptb200 {
 
@@ -239,9 +240,8 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t spp = 4LL * p->samples;
     const int64_t pix_begin = static_cast<int64_t>(x0) * p->height, pix_end = static_cast<int64_t>(x1) * p->height;
-    // Tile = whole pixels, up to 64 Mi paths (2.4 GB of workspace: rays 24 B + colours 12 B per path, which stay
-    // in HBM between the three kernels of a tile and never travel to the host).  Large tiles keep the persistent
-    // trace kernel's tail and the launch gaps below a few percent.
+    // Tile = whole pixels, up to 64 Mi paths (0.8 GB of workspace).  Large tiles keep the launch gaps and the persistent
+    // kernel's tail below a few percent.
     const int64_t target_paths = 64LL << 20;
     int64_t tile_pix = target_paths / spp;
     if (tile_pix < 1)
@@ -249,17 +249,16 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
     if (tile_pix > pix_end - pix_begin)
         tile_pix = pix_end - pix_begin;
     const int64_t tile_paths = tile_pix * spp;
+    // Rays are generated inside the trace kernel (straight into its shared-memory ring) and never exist in HBM; only the
+    // per-path colours of a tile (12 B/path) are materialised between the trace and the resolve kernel.
     PtArena *arena = nullptr;
-    const size_t ray_bytes = sizeof(float) * 6 * static_cast<size_t>(tile_paths), col_bytes = sizeof(float) * 3 * static_cast<size_t>(tile_paths);
-    if ((rc = workspace(ray_bytes + col_bytes + 4096, &arena)) != PTB200_OK)
+    const size_t col_bytes = sizeof(float) * 3 * static_cast<size_t>(tile_paths);
+    if ((rc = workspace(col_bytes + 4096, &arena)) != PTB200_OK)
         return rc;
-    float *rays = static_cast<float *>(ptb200_arena_alloc(arena, ray_bytes));
+    float *rays = nullptr;
     float *cols = static_cast<float *>(ptb200_arena_alloc(arena, col_bytes));
-    if (rays == nullptr || cols == nullptr) {
-        ptb200_arena_free(arena, rays);
-        ptb200_arena_free(arena, cols);
+    if (cols == nullptr)
         return PTB200_ENOMEM;
-    }
     cudaError_t e = cudaSuccess;
     if (stats != nullptr)
         e = cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), stream);
@@ -268,14 +267,13 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
         const int64_t npix = (pix_end - q < tile_pix) ? pix_end - q : tile_pix;
         const int64_t m = npix * spp;
         const double *u = uniforms ? uniforms + 2 * (q - pix_begin) * spp : nullptr;
-        if ((e = gen_rays(stream, *p, u, seed, q * spp, m, rays)) != cudaSuccess)
-            break;
+        const RayGenSource gen = make_raygen_source(*p, u, seed, q * spp, m);
         // the tile is its own m-path problem for the trace kernel
         if (mp != nullptr)
-            e = trace_materials(stream, *p, *mp, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m, static_cast<uint64_t>(q * spp), seg_stat,
-                                tree);
+            e = trace_materials(stream, *p, *mp, nullptr, reinterpret_cast<const float *>(spheres), cols, m, 0, m, static_cast<uint64_t>(q * spp), seg_stat,
+                                tree, &gen);
         else
-            e = trace_paths(stream, *p, rays, reinterpret_cast<const float *>(spheres), cols, m, 0, m, seg_stat);
+            e = trace_paths(stream, *p, nullptr, reinterpret_cast<const float *>(spheres), cols, m, 0, m, seg_stat, &gen);
         if (e != cudaSuccess)
             break;
         if ((e = resolve_pixels(stream, *p, cols, m, q, npix, image, x0, x1 - x0, gamma)) != cudaSuccess)

@@ -12,15 +12,18 @@ constexpr int kTraceThreads = 256;
 
 // trace_kernels.cu -- paths [first, first+count) of N-path SoA buffers; stats (nullable, device) gets
 // the number of ray segments actually traced added to it.
+// gen (nullable): generate the rays inside the kernel instead of reading `rays` (which may then be NULL); element
+// `first` of the launch is the generator's element 0.
+struct RayGenSource;
 cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *rays, const float *spheres, float *colors, int64_t n,
-                        int64_t first, int64_t count, unsigned long long *stats);
+                        int64_t first, int64_t count, unsigned long long *stats, const RayGenSource *gen = nullptr);
 
 // trace_kernels.cu -- material extension (pt_material.cuh): spheres is the 11-row SoA; element i of the slice has RNG
 // path index path0 + (i - first).
 // tree (nullable): a BVH built by ptb200_bvh_build over the same spheres; then `spheres` may be NULL.
 cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMaterialParams &mp, const float *rays, const float *spheres,
                             float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats,
-                            const PtBvh *tree = nullptr);
+                            const PtBvh *tree = nullptr, const RayGenSource *gen = nullptr);
 
 // bvh.cu
 struct BvhScene;

@@ -16,6 +16,7 @@
 #include "pt_device.cuh"
 #include "pt_host.h"
 #include "pt_material.cuh"
+#include "pt_raygen.cuh"
 
 namespace ptb200 {
 
@@ -68,7 +69,20 @@ constexpr int kChunkBatches = 64;  // a warp claims 64 batches = 2048 consecutiv
 // with a static split the slowest warp set the kernel's duration and a third of the warp slots sat idle at the end),
 // fetched by coalesced cp.async batches of 32 rays into a shared-memory ring kRingBatches batches ahead of use, and
 // handed to the lanes that ask for a path in ballot-rank order, i.e. consecutive indices to the lanes of one swap.
-struct PathFeeder {
+// Out of line on purpose: the binary64 generator needs ~40 registers of its own and runs once per 32 paths; as a call it
+// borrows them for a moment instead of raising the register count (and lowering the occupancy) of the whole kernel.
+// The generator's parameters live in the constant bank (staged per launch next to the scene, same stream ordering).
+static __constant__ RayGenSource c_gen;
+
+static __device__ __noinline__ void generate_ray_to_ring(unsigned int path, float *slot) {
+    float r[6];
+    generate_ray(c_gen, static_cast<long long>(path), r);
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+        slot[c * kRing] = r[c];
+}
+
+template <bool GEN> struct PathFeeder {
     const TracePlanes &pl;
     float *ring;
     unsigned long long *counter;
@@ -76,7 +90,9 @@ struct PathFeeder {
     unsigned int chunk_even, chunk_odd;  // first path of the chunk with even / odd sequence number (>= count: no such chunk)
     unsigned int issued, head;
 
-    __device__ __forceinline__ PathFeeder(const TracePlanes &planes, float *ring_, unsigned long long *counter_, unsigned int count_, unsigned int lane_)
+    // GEN: rays are generated straight into the ring (c_gen) and never exist in HBM; pl.ray is unused then.
+    __device__ __forceinline__ PathFeeder(const TracePlanes &planes, float *ring_, unsigned long long *counter_, unsigned int count_,
+                                          unsigned int lane_)
         : pl(planes), ring(ring_), counter(counter_), count(count_), lane(lane_), issued(0), head(0) {
         chunk_even = chunk_odd = count_;
         for (int b = 0; b < kRingBatches; b++)
@@ -102,11 +118,16 @@ struct PathFeeder {
         const unsigned int path = path_of(seq);
         if (path < count) {
             const unsigned int s = seq & (kRing - 1);
+            if (GEN) {
+                generate_ray_to_ring(path, ring + s);
+            } else {
 #pragma unroll
-            for (int c = 0; c < 6; c++)
-                __pipeline_memcpy_async(ring + c * kRing + s, pl.ray[c] + path, sizeof(float));
+                for (int c = 0; c < 6; c++)
+                    __pipeline_memcpy_async(ring + c * kRing + s, pl.ray[c] + path, sizeof(float));
+            }
         }
-        __pipeline_commit();
+        if (!GEN)
+            __pipeline_commit();
         issued++;
     }
     // Called by the whole warp when at least one lane wants a path.  Lanes that get one receive its index and a pointer
@@ -117,8 +138,9 @@ struct PathFeeder {
         const unsigned int seq = head + __popc(wmask & lt);
         path = path_of(seq);
         const bool got = want && path < count;
-        __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
-        __syncwarp();              // ... and is visible to the other lanes of the warp
+        if (!GEN)
+            __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
+        __syncwarp();                  // ... and is visible to the other lanes of the warp
         slot = ring + (seq & (kRing - 1));
         head += __popc(wmask);
         return got;
@@ -133,7 +155,7 @@ struct PathFeeder {
 #ifndef PTB_BLOCKS_PER_SM
 #define PTB_BLOCKS_PER_SM 5
 #endif
-template <int NS, bool EARLY>
+template <int NS, bool EARLY, bool GEN>
 __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                        int depth, int nsph, int stride, int light, float scale, float one,
                                                                        unsigned long long *__restrict__ stats, unsigned long long *work_counter) {
@@ -148,7 +170,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
     // flight) the colours they store share cache lines.  See PathFeeder for how paths reach the warp.
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    PathFeeder feed(pl, reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
+    PathFeeder<GEN> feed(pl, reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
 
     PathState p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -209,7 +231,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
 
 // ---- material extension kernel (pt_material.cuh) ------------------------------------------------------------------
 // Same persistent warps, ring and ballot-ranked regeneration; one iteration = one bounce of material_bounce().
-template <int NS, bool BVH>
+template <int NS, bool BVH, bool GEN>
 __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                            int max_depth, int rr_start, int nsph, int stride, float eps, float one,
                                                                            unsigned long long seed, unsigned long long path0,
@@ -225,7 +247,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
     }
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    PathFeeder feed(pl, reinterpret_cast<float *>(smem + (BVH ? 0 : 3 * nsph)) + warp_in_block * (6 * kRing), work_counter, count, lane);
+    PathFeeder<GEN> feed(pl, reinterpret_cast<float *>(smem + (BVH ? 0 : 3 * nsph)) + warp_in_block * (6 * kRing), work_counter, count, lane);
 
     MatPath p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -285,7 +307,7 @@ namespace {
 struct DeviceState {
     bool init = false;
     int sm_count = 0;
-    int blocks_per_sm[4] = {0, 0, 0, 0};  // [NS8?][EARLY?]
+    int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [GEN?][NS8?][EARLY?]
     SceneConst *scene_alias = nullptr;
     int *zero_ok_alias = nullptr;
     unsigned long long *work_counter = nullptr;  // chunk dispenser of the persistent kernels (reset before every launch)
@@ -298,8 +320,13 @@ constexpr int kMaxDevices = 64;
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
 
-template <int NS, bool EARLY> cudaError_t occupancy(int *out, size_t smem) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, trace_paths_kernel<NS, EARLY>, kTraceThreads, smem);
+template <int NS, bool EARLY, bool GEN> cudaError_t occupancy(int *out, size_t smem) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, trace_paths_kernel<NS, EARLY, GEN>, kTraceThreads, smem);
+}
+
+// Stages the ray generator's parameters (fused generate-and-trace launches); caller holds g_mu and has ordered the stream.
+cudaError_t stage_gen(cudaStream_t stream, const RayGenSource &g) {
+    return cudaMemcpyToSymbolAsync(c_gen, &g, sizeof g, 0, cudaMemcpyHostToDevice, stream);
 }
 
 cudaError_t ensure_device_state(DeviceState **out) {
@@ -327,13 +354,13 @@ cudaError_t ensure_device_state(DeviceState **out) {
     return cudaSuccess;
 }
 
-template <int NS, bool EARLY>
+template <int NS, bool EARLY, bool GEN>
 cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays, const float *spheres, float *colors, int64_t n,
-                         int64_t first, int64_t count, const PtParams &p, unsigned long long *stats) {
+                         int64_t first, int64_t count, const PtParams &p, unsigned long long *stats, const RayGenSource *gen) {
     const size_t smem = sizeof(float4) * 2 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
-    int &occ = s.blocks_per_sm[(NS > 0 ? 2 : 0) + (EARLY ? 1 : 0)];
+    int &occ = s.blocks_per_sm[(GEN ? 4 : 0) + (NS > 0 ? 2 : 0) + (EARLY ? 1 : 0)];
     if (occ == 0 || NS == 0) {
-        cudaError_t e = occupancy<NS, EARLY>(&occ, smem);
+        cudaError_t e = occupancy<NS, EARLY, GEN>(&occ, smem);
         if (e != cudaSuccess)
             return e;
         if (occ < 1)
@@ -345,7 +372,7 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
         const int64_t m = (first + count - a < kMaxPerLaunch) ? first + count - a : kMaxPerLaunch;
         TracePlanes pl;
         for (int c = 0; c < 6; c++)
-            pl.ray[c] = rays + c * n + a;
+            pl.ray[c] = GEN ? nullptr : rays + c * n + a;
         for (int c = 0; c < 3; c++)
             pl.col[c] = colors + c * n + a;
         const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
@@ -353,9 +380,16 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
         cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess)
             return e;
-        trace_paths_kernel<NS, EARLY><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), p.depth, p.sphere_count,
-                                                                             p.sphere_stride, p.light_index, p.emission_scale, 1.0f, stats,
-                                                                             s.work_counter);
+        if (GEN) {  // element i of this launch is element (a - first) + i of the generator's range
+            RayGenSource g = *gen;
+            const int64_t off = a - first;
+            g = make_raygen_source_shifted(g, off, m);
+            if ((e = stage_gen(stream, g)) != cudaSuccess)
+                return e;
+        }
+        trace_paths_kernel<NS, EARLY, GEN><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), p.depth,
+                                                                                  p.sphere_count, p.sphere_stride, p.light_index, p.emission_scale,
+                                                                                  1.0f, stats, s.work_counter);
         e = cudaGetLastError();
         if (e != cudaSuccess)
             return e;
@@ -366,7 +400,7 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
 }  // namespace
 
 cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *rays, const float *spheres, float *colors, int64_t n,
-                        int64_t first, int64_t count, unsigned long long *stats) {
+                        int64_t first, int64_t count, unsigned long long *stats, const RayGenSource *gen) {
     if (count <= 0)
         return cudaSuccess;
     std::lock_guard<std::mutex> lock(g_mu);
@@ -394,11 +428,15 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
     }();
     const bool early = !(p.flags & PTB200_F_FIXED_DEPTH) && p.depth >= min_early_depth;
     if (p.sphere_count == 8)
-        e = early ? launch_trace<8, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats)
-                  : launch_trace<8, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats);
+        e = early ? (gen ? launch_trace<8, true, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen)
+                         : launch_trace<8, true, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen))
+                  : (gen ? launch_trace<8, false, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen)
+                         : launch_trace<8, false, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen));
     else
-        e = early ? launch_trace<0, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats)
-                  : launch_trace<0, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats);
+        e = early ? (gen ? launch_trace<0, true, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen)
+                         : launch_trace<0, true, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen))
+                  : (gen ? launch_trace<0, false, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen)
+                         : launch_trace<0, false, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen));
     if (e != cudaSuccess)
         return e;
     if ((e = cudaEventRecord(s->scene_free, stream)) != cudaSuccess)
@@ -410,7 +448,8 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
 
 
 cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtMaterialParams &mp, const float *rays, const float *spheres_in,
-                            float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats, const PtBvh *tree) {
+                            float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats, const PtBvh *tree,
+                            const RayGenSource *gen) {
     if (count <= 0)
         return cudaSuccess;
     // With a tree, the constant bank and the kernel's brute-force loop see only the huge spheres (compacted SoA, stride 1024).
@@ -441,9 +480,10 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
     const size_t smem = (use_tree ? 0 : sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count)) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
     const bool ten = !use_tree && (p.sphere_count == 9 || p.sphere_count == 10);  // smallpt's scene: unrolled pairs (index 9 is padding)
     int occ = 0;
-    if ((e = use_tree ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, true>, kTraceThreads, smem)
-              : ten   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<10, false>, kTraceThreads, smem)
-                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, false>, kTraceThreads, smem)) != cudaSuccess)
+    // the fused-generation variants have the same resource footprint as the SoA ones (the generator is an out-of-line call)
+    if ((e = use_tree ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, true, false>, kTraceThreads, smem)
+              : ten   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<10, false, false>, kTraceThreads, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, false, false>, kTraceThreads, smem)) != cudaSuccess)
         return e;
     if (occ < 1)
         occ = 1;
@@ -462,18 +502,23 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
             return e;
         const unsigned int mm = static_cast<unsigned int>(m);
         const unsigned long long pp = path0 + static_cast<uint64_t>(a - first);
-        if (use_tree)
-            trace_materials_kernel<0, true><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
-                                                                                   p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh,
-                                                                                   s->work_counter);
-        else if (ten)
-            trace_materials_kernel<10, false><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
-                                                                                     p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh,
-                                                                                   s->work_counter);
-        else
-            trace_materials_kernel<0, false><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,
-                                                                                    p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh,
-                                                                                   s->work_counter);
+        if (gen != nullptr) {
+            pl = TracePlanes{{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {pl.col[0], pl.col[1], pl.col[2]}};
+            if ((e = stage_gen(stream, make_raygen_source_shifted(*gen, a - first, m))) != cudaSuccess)
+                return e;
+        }
+#define PTB_LAUNCH_MAT(NSV, BVHV, GENV)                                                                                                        \
+    trace_materials_kernel<NSV, BVHV, GENV><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,     \
+                                                                                   p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh, \
+                                                                                   s->work_counter)
+        if (use_tree) {
+            if (gen) PTB_LAUNCH_MAT(0, true, true); else PTB_LAUNCH_MAT(0, true, false);
+        } else if (ten) {
+            if (gen) PTB_LAUNCH_MAT(10, false, true); else PTB_LAUNCH_MAT(10, false, false);
+        } else {
+            if (gen) PTB_LAUNCH_MAT(0, false, true); else PTB_LAUNCH_MAT(0, false, false);
+        }
+#undef PTB_LAUNCH_MAT
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }
