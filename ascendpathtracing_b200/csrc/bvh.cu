@@ -141,6 +141,38 @@ __global__ void fit_kernel(const int *__restrict__ vals, const int *__restrict__
     }
 }
 
+// Float child boxes -> the 32-byte traversal nodes of pt_bvh.cuh: 16-bit grid planes, rounded outwards and grown by
+// kGridGrow units (the slack the one-FFMA slab test needs, see pt_bvh.cuh).  The grid was sized on the host so that no
+// plane ever clamps.
+struct GridMap {
+    float lo[3], scale[3];
+};
+
+__device__ __forceinline__ unsigned int quantize_pair(float vlo, float vhi, float glo, float gs) {
+    const float a = floorf((vlo - glo) * gs) - static_cast<float>(kGridGrow);
+    const float b = ceilf((vhi - glo) * gs) + static_cast<float>(kGridGrow);
+    const unsigned int qa = static_cast<unsigned int>(fminf(fmaxf(a, 0.0f), kGridMax));
+    const unsigned int qb = static_cast<unsigned int>(fminf(fmaxf(b, 0.0f), kGridMax));
+    return qa | (qb << 16);
+}
+
+__global__ void quantize_kernel(const BvhNode *__restrict__ nodes, int n_nodes, GridMap g, QNode *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes)
+        return;
+    const BvhNode nd = nodes[i];
+    QNode q;
+    q.lx = quantize_pair(nd.a.x, nd.a.w, g.lo[0], g.scale[0]);
+    q.ly = quantize_pair(nd.a.y, nd.b.x, g.lo[1], g.scale[1]);
+    q.lz = quantize_pair(nd.a.z, nd.b.y, g.lo[2], g.scale[2]);
+    q.left = nd.left;
+    q.rx = quantize_pair(nd.b.z, nd.c.y, g.lo[0], g.scale[0]);
+    q.ry = quantize_pair(nd.b.w, nd.c.z, g.lo[1], g.scale[1]);
+    q.rz = quantize_pair(nd.c.x, nd.c.w, g.lo[2], g.scale[2]);
+    q.right = nd.right;
+    out[i] = q;
+}
+
 // Nearest hit only (tests / diagnostics): big spheres brute force + tree, the reference's (t, index) semantics.
 __global__ void first_hit_kernel(BvhScene sc, const float *__restrict__ rays, int64_t n, float eps, float *__restrict__ tmin_out,
                                  int *__restrict__ idx_out) {
@@ -173,15 +205,19 @@ struct PtBvh {
     int device = 0;
     int n = 0, stride = 0, n_big = 0, n_small = 0;
     float e_disc = 0.0f;
-    BvhNode *nodes = nullptr;
+    QNode *qnodes = nullptr;
+    int *small_index = nullptr;
+    float glo[3] = {0, 0, 0}, gscale[3] = {1, 1, 1};
     float4 *geom = nullptr, *color = nullptr, *emission = nullptr;
     int *big_index = nullptr;
     float *big_soa = nullptr;  // [11][16] SoA of the big spheres for the constant-bank pack
     int only_leaf = 0;
     BvhScene scene() const {
         BvhScene s;
-        s.nodes = nodes, s.geom = geom, s.color = color, s.emission = emission, s.big_index = big_index;
+        s.qnodes = qnodes, s.geom = geom, s.color = color, s.emission = emission, s.big_index = big_index, s.small_index = small_index;
         s.n_big = n_big, s.n_small = n_small, s.root = 0, s.only_leaf = only_leaf;
+        for (int c = 0; c < 3; c++)
+            s.glo[c] = glo[c], s.gscale[c] = gscale[c];
         return s;
     }
 };
@@ -198,7 +234,8 @@ extern "C" {
 int ptb200_bvh_destroy(PtBvh *b) {
     if (b == nullptr)
         return PTB200_OK;
-    cudaFree(b->nodes);
+    cudaFree(b->qnodes);
+    cudaFree(b->small_index);
     cudaFree(b->geom);
     cudaFree(b->color);
     cudaFree(b->emission);
@@ -263,9 +300,20 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
             ext[c] = static_cast<float>(dlt > 0 ? dlt : 1.0);
         }
     b->e_disc = static_cast<float>(diag2 * (1.0 / 524288.0));  // 2^-19 D^2
+    // 16-bit grid of the traversal nodes: covers every padded box (pad <= sqrt(E) + 1e-3 * 100 + 1e-3) with room for the
+    // outward rounding and the kGridGrow units, so no plane ever clamps.
+    if (!small.empty()) {
+        const double margin = std::sqrt(static_cast<double>(b->e_disc)) + 1.2;
+        for (int c = 0; c < 3; c++) {
+            const double glo = static_cast<double>(lo[c]) - margin, ghi = static_cast<double>(hi[c]) + margin;
+            b->glo[c] = static_cast<float>(glo);
+            b->gscale[c] = static_cast<float>((65535.0 - 4.0 * (kGridGrow + 2)) / (ghi - static_cast<double>(b->glo[c])));
+        }
+    }
 
     auto dmalloc = [&](void **p, size_t bytes) { return e == cudaSuccess ? (e = cudaMalloc(p, bytes ? bytes : 16)) : e; };
-    int *d_small = nullptr, *d_vals_in = nullptr, *d_vals = nullptr, *d_leaf_parent = nullptr;
+    BvhNode *d_nodes = nullptr;
+    int *d_vals_in = nullptr, *d_vals = nullptr, *d_leaf_parent = nullptr;
     unsigned int *d_keys_in = nullptr, *d_keys = nullptr, *d_visits = nullptr;
     Aabb *d_own = nullptr;
     void *d_tmp = nullptr;
@@ -275,8 +323,10 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
     dmalloc(reinterpret_cast<void **>(&b->emission), sizeof(float4) * count);
     dmalloc(reinterpret_cast<void **>(&b->big_index), sizeof(int) * std::max(nb, 1));
     dmalloc(reinterpret_cast<void **>(&b->big_soa), sizeof(float) * 11 * 1024);
-    dmalloc(reinterpret_cast<void **>(&b->nodes), sizeof(BvhNode) * std::max(ns - 1, 1));
-    dmalloc(reinterpret_cast<void **>(&d_small), sizeof(int) * std::max(ns, 1));
+    dmalloc(reinterpret_cast<void **>(&d_nodes), sizeof(BvhNode) * std::max(ns - 1, 1));
+    dmalloc(reinterpret_cast<void **>(&b->qnodes), sizeof(QNode) * std::max(ns - 1, 1));
+    dmalloc(reinterpret_cast<void **>(&b->small_index), sizeof(int) * std::max(ns, 1));
+    int *const d_small = b->small_index;
     dmalloc(reinterpret_cast<void **>(&d_keys_in), sizeof(unsigned int) * std::max(ns, 1));
     dmalloc(reinterpret_cast<void **>(&d_keys), sizeof(unsigned int) * std::max(ns, 1));
     dmalloc(reinterpret_cast<void **>(&d_vals_in), sizeof(int) * std::max(ns, 1));
@@ -313,17 +363,24 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
         if (e == cudaSuccess)
             e = cudaMemsetAsync(d_visits, 0, sizeof(unsigned int) * ns, stream);
         if (e == cudaSuccess) {
-            hierarchy_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(d_keys, d_vals, ns, b->nodes, d_leaf_parent);
+            hierarchy_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(d_keys, d_vals, ns, d_nodes, d_leaf_parent);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) {
-            fit_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(d_vals, d_leaf_parent, ns, b->geom, b->e_disc, b->nodes, d_own, d_visits);
+            fit_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(d_vals, d_leaf_parent, ns, b->geom, b->e_disc, d_nodes, d_own, d_visits);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) {
+            GridMap g;
+            for (int c = 0; c < 3; c++)
+                g.lo[c] = b->glo[c], g.scale[c] = b->gscale[c];
+            quantize_kernel<<<(ns - 1 + 255) / 256, 256, 0, stream>>>(d_nodes, ns - 1, g, b->qnodes);
             e = cudaGetLastError();
         }
     }
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(stream);
-    cudaFree(d_small), cudaFree(d_keys_in), cudaFree(d_keys), cudaFree(d_vals_in), cudaFree(d_vals), cudaFree(d_leaf_parent), cudaFree(d_visits),
+    cudaFree(d_nodes), cudaFree(d_keys_in), cudaFree(d_keys), cudaFree(d_vals_in), cudaFree(d_vals), cudaFree(d_leaf_parent), cudaFree(d_visits),
         cudaFree(d_own), cudaFree(d_tmp);
     if (e != cudaSuccess) {
         ptb200_bvh_destroy(b);

@@ -1,27 +1,42 @@
 // Sphere BVH for scenes beyond the constant bank (BASELINE config C4: 10 k spheres).
 //
 // Requirement: the nearest hit found through the BVH equals the brute-force loop's (same t bits, same index, lowest
-// index on ties), for every ray whose origin lies in the scene.  The brute-force test is decided by rounding noise near
-// grazing incidence (disc = b^2 - c carries an absolute error of a few ulp(|oc|^2)), so a sphere can be "hit" by a ray that
+// index on ties), for every ray.  The brute-force test is decided by rounding noise near grazing incidence
+// (disc = b^2 - c carries an absolute error of a few ulp(|oc|^2)), so a sphere can be "hit" by a ray that
 // geometrically misses it by up to sqrt(r^2 + E) - r.  Hence
 //   * huge spheres (r^2 >= kBigR2: the 1e5-radius walls, the 600-radius light) never enter the tree: they stay in a
 //     brute-force list in the constant bank, tested pairwise with packed f32x2 like the 8-sphere scene;
 //   * every other sphere's box is its geometric box grown by pad = sqrt(r^2 + E) - r + 1e-3 r + 1e-3, E = 2^-19 * D^2 with
 //     D the diagonal of the scene's bounds (a 16x margin over the worst-case discriminant error at that distance);
-//   * leaves run the exact scalar test (sphere_t), candidates are merged with the (t, index) order of the reference.
+//   * leaves run the exact scalar test, candidates are merged with the (t, index) order of the reference.
 //
-// Layout: LBVH (Morton order, Karras 2012).  An internal node stores BOTH child boxes and both child references in
-// 64 bytes (4 x LDG.128 served from L1/L2), so one fetch decides two subtrees; a reference < 0 is a leaf (~ref = sphere).
-// Traversal: per-lane stack of 32 entries in local memory, near child first.
+// What bounds traversal on B200 (ncu, profiles/r2_c4_*): incoherent rays make every node fetch touch one cache line per
+// lane, and L1 looks up one line per clock per SM -- the tag stage, not the arithmetic, is the limit.  So a node is
+// 32 bytes = two LDG.128 (one per child: 6 x 16-bit box planes + reference), half the lines of the float layout:
+//   * planes are quantised to a 16-bit grid over the tree's bounds, rounded outwards and grown by kGridGrow units;
+//   * decoding costs nothing: PRMT drops the 16 bits into the mantissa of 2^23 (0x4B000000 | q = 2^23 + q exactly), and
+//     the slab distance is ONE FFMA, t = (2^23 + q) * id + c with id = 1 / (d * scale) and c = -(2^23 + round(og)) * id
+//     (og = ray origin in grid units).  Rounding og to an integer and rounding c each move a plane by at most 0.504 grid
+//     units and the FMA's own rounding by less than 0.13 (origins within 2^21 units), together < kGridGrow = 2 minus the
+//     slack spent on the float evaluation of floor/ceil at build time: the test stays conservative.  A relative error of
+//     id scales both terms alike, so MUFU.RCP is good enough for it;
+//   * the near/far plane of each axis is picked by the PRMT selector (sign of d), not by min/max afterwards.
+// Origins further than 2^21 grid units from the tree (64 scene widths) fall back to an exact loop over all spheres.
+//
+// Layout: LBVH (Morton order, Karras 2012); a reference < 0 is a leaf (~ref = sphere).  Traversal: near child first,
+// leaves tested inline (at most two per step, one code copy), stack policy supplied by the caller.
 #pragma once
 #include "pt_device.cuh"
 
 namespace ptb200 {
 
-constexpr float kBigR2 = 1.0e4f;  // radius >= 100 stays out of the tree
-constexpr int kBvhStack = 48;
+constexpr float kBigR2 = 1.0e4f;    // radius >= 100 stays out of the tree
+constexpr int kBvhStack = 64;       // Karras depth <= 30 key bits + 24 index bits (ptb200_bvh_build caps the count at 2^24)
+constexpr int kGridGrow = 2;        // grid units added on every side of a quantised box (see above)
+constexpr float kGridMax = 65535.0f;
+constexpr float kGridFar = 2097152.0f;  // 2^21: |og| beyond this -> exact fallback
 
-struct BvhNode {  // 64 bytes
+struct BvhNode {  // build-time node, float boxes (bvh.cu), 64 bytes
     float4 a;     // l.min.x l.min.y l.min.z l.max.x
     float4 b;     // l.max.y l.max.z r.min.x r.min.y
     float4 c;     // r.min.z r.max.x r.max.y r.max.z
@@ -29,39 +44,158 @@ struct BvhNode {  // 64 bytes
     int parent, pad;
 };
 
+struct QNode {  // traversal node, 32 bytes: word c of a child = lo_c | hi_c << 16 in grid units
+    unsigned int lx, ly, lz;
+    int left;
+    unsigned int rx, ry, rz;
+    int right;
+};
+
 struct BvhScene {
-    const BvhNode *nodes;    // n_small - 1 internal nodes (none when n_small <= 1)
+    const QNode *qnodes;     // n_small - 1 internal nodes (none when n_small <= 1)
     const float4 *geom;      // per sphere (original index): x, y, z, -r^2
     const float4 *color;     // r, g, b, material
     const float4 *emission;  // r, g, b, -
     const int *big_index;    // original indices of the spheres kept in the constant bank (ascending)
+    const int *small_index;  // original indices of the spheres in the tree (ascending): the exact fallback's list
     int n_big, n_small, root, only_leaf;  // root: internal node 0 or, when n_small == 1, the leaf reference only_leaf
+    float glo[3], gscale[3];              // grid = (world - glo) * gscale
 };
 
-// Slab test against a padded box; NaN-tolerant min/max order (a NaN from 0 * inf falls out).
-__device__ __forceinline__ bool hit_box(float ox, float oy, float oz, float ix, float iy, float iz, float lx, float ly, float lz, float hx,
-                                        float hy, float hz, float tbest, float &tnear) {
-    const float tx1 = (lx - ox) * ix, tx2 = (hx - ox) * ix;
-    const float ty1 = (ly - oy) * iy, ty2 = (hy - oy) * iy;
-    const float tz1 = (lz - oz) * iz, tz2 = (hz - oz) * iz;
-    float tn = fminf(tx1, tx2), tf = fmaxf(tx1, tx2);
-    tn = fmaxf(tn, fminf(ty1, ty2)), tf = fminf(tf, fmaxf(ty1, ty2));
-    tn = fmaxf(tn, fminf(tz1, tz2)), tf = fminf(tf, fmaxf(tz1, tz2));
+// Per-ray traversal constants (9 registers).
+struct BvhRay {
+    float idx, idy, idz;          // 1 / (d * gscale)
+    float cx, cy, cz;             // -(2^23 + round(og)) * id
+    unsigned int sx, sy, sz;      // PRMT selectors of the near plane per axis (far = near ^ 0x22)
+    bool far_origin;              // origin outside the range the 2^23 trick covers
+};
+
+__device__ __forceinline__ BvhRay bvh_ray(const BvhScene &sc, float ox, float oy, float oz, float dx, float dy, float dz) {
+    BvhRay r;
+    const float ogx = __fmul_rn(__fsub_rn(ox, sc.glo[0]), sc.gscale[0]);
+    const float ogy = __fmul_rn(__fsub_rn(oy, sc.glo[1]), sc.gscale[1]);
+    const float ogz = __fmul_rn(__fsub_rn(oz, sc.glo[2]), sc.gscale[2]);
+    r.far_origin = !(fmaxf(fmaxf(fabsf(ogx), fabsf(ogy)), fabsf(ogz)) <= kGridFar);  // NaN origins too
+    r.idx = mufu_rcp(__fmul_rn(dx, sc.gscale[0]));
+    r.idy = mufu_rcp(__fmul_rn(dy, sc.gscale[1]));
+    r.idz = mufu_rcp(__fmul_rn(dz, sc.gscale[2]));
+    r.cx = -__fmul_rn(__fadd_rn(ogx, 8388608.0f), r.idx);
+    r.cy = -__fmul_rn(__fadd_rn(ogy, 8388608.0f), r.idy);
+    r.cz = -__fmul_rn(__fadd_rn(ogz, 8388608.0f), r.idz);
+    r.sx = dx < 0.0f ? 0x7632u : 0x7610u;
+    r.sy = dy < 0.0f ? 0x7632u : 0x7610u;
+    r.sz = dz < 0.0f ? 0x7632u : 0x7610u;
+    return r;
+}
+
+// Slab test of one quantised child box.  NaN planes (0 * inf, inf - inf on an axis the ray does not move along) drop out
+// of the 3-input min/max, which only makes the test more permissive.
+__device__ __forceinline__ bool hit_qbox(const BvhRay &r, unsigned int wx, unsigned int wy, unsigned int wz, float tbest, float &tnear) {
+    const float nx = __fmaf_rn(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx)), r.idx, r.cx);
+    const float ny = __fmaf_rn(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy)), r.idy, r.cy);
+    const float nz = __fmaf_rn(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz)), r.idz, r.cz);
+    const float fx = __fmaf_rn(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx ^ 0x22u)), r.idx, r.cx);
+    const float fy = __fmaf_rn(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy ^ 0x22u)), r.idy, r.cy);
+    const float fz = __fmaf_rn(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz ^ 0x22u)), r.idz, r.cz);
+    const float tn = fmaxf(fmaxf(nx, ny), nz);
+    const float tf = fminf(fminf(fx, fy), fz);
     tnear = tn;
     return tf >= fmaxf(tn, 0.0f) && tn <= tbest;
 }
 
+// Exact leaf test (sphere_t's arithmetic, rt_helper.h:255-370) with the reference's (t, index) merge: smaller t, then
+// lower index.  A negative or NaN discriminant is a miss (sqrt gives NaN, both compares fail, t = 1e20) and a miss can
+// never replace the current best, so the square root is skipped for it.
 __device__ __forceinline__ void bvh_leaf(const BvhScene &sc, int sphere, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
                                          float &tmin, int &idx) {
     const float4 g = __ldg(sc.geom + sphere);
-    const float t = sphere_t(ox, oy, oz, dx, dy, dz, g.x, g.y, g.z, g.w, eps);
-    if (t < tmin || (t == tmin && t < kMiss && sphere < idx)) {  // the reference's order: smaller t, then lower index
-        tmin = t;
-        idx = sphere;
+    const float ocx = __fsub_rn(g.x, ox);
+    const float ocy = __fsub_rn(g.y, oy);
+    const float ocz = __fsub_rn(g.z, oz);
+    const float b = __fadd_rn(__fadd_rn(__fmul_rn(ocx, dx), __fmul_rn(ocy, dy)), __fmul_rn(ocz, dz));
+    const float c = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ocx, ocx), __fmul_rn(ocy, ocy)), __fmul_rn(ocz, ocz)), g.w);
+    const float disc = __fsub_rn(__fmul_rn(b, b), c);
+    if (disc >= 0.0f) {
+        const float s = __fsqrt_rn(disc);
+        const float t0 = __fsub_rn(b, s);
+        const float t1 = __fadd_rn(b, s);
+        float t = (t0 > eps) ? t0 : t1;
+        t = (t > eps) ? t : kMiss;
+        if (t < tmin || (t == tmin && t < kMiss && sphere < idx)) {
+            tmin = t;
+            idx = sphere;
+        }
     }
 }
 
+// One traversal step at internal node `node`: tests both children, runs the exact test on hit leaves, and leaves the next
+// internal node in `node` (or -1 when the stack ran empty: traversal finished).
+// Stack: push(int), bool pop(int&).  Ray: ox(), oy(), ... accessors of the exact ray for the leaf tests.
+template <class Stack, class Ray>
+__device__ __forceinline__ void bvh_step(const BvhScene &sc, const BvhRay &r, const Ray &ray, float eps, int &node, float &tmin, int &idx, Stack &st) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(sc.qnodes + node);
+    const uint4 L = __ldg(q), R = __ldg(q + 1);
+    const int left = static_cast<int>(L.w), right = static_cast<int>(R.w);
+    float tl, tr;
+    bool hl = hit_qbox(r, L.x, L.y, L.z, tmin, tl);
+    bool hr = hit_qbox(r, R.x, R.y, R.z, tmin, tr);
+    int leaf_a = (hl && left < 0) ? ~left : -1;
+    int leaf_b = (hr && right < 0) ? ~right : -1;
+    hl = hl && left >= 0;
+    hr = hr && right >= 0;
+    if (leaf_a < 0) {
+        leaf_a = leaf_b;
+        leaf_b = -1;
+    }
+    while (leaf_a >= 0) {  // at most two rounds; one copy of the leaf code for the warp to share
+        bvh_leaf(sc, leaf_a, ray.ox(), ray.oy(), ray.oz(), ray.dx(), ray.dy(), ray.dz(), eps, tmin, idx);
+        leaf_a = leaf_b;
+        leaf_b = -1;
+    }
+    if (hl && hr) {  // near child first, far child on the stack
+        const bool lfirst = tl <= tr;
+        st.push(lfirst ? right : left);
+        node = lfirst ? left : right;
+    } else if (hl) {
+        node = left;
+    } else if (hr) {
+        node = right;
+    } else if (!st.pop(node)) {
+        node = -1;
+    }
+}
+
+// Exact fallback for rays the quantised traversal does not cover: every sphere of the tree, ascending index.
+static __device__ __noinline__ void bvh_all_leaves(const BvhScene &sc, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
+                                                   float &tmin, int &idx) {
+    for (int k = 0; k < sc.n_small; k++)
+        bvh_leaf(sc, __ldg(sc.small_index + k), ox, oy, oz, dx, dy, dz, eps, tmin, idx);
+}
+
+struct LocalStack {  // per-lane stack in local memory
+    int v[kBvhStack];
+    int sp = 0;
+    __device__ __forceinline__ void push(int x) { v[sp++] = x; }
+    __device__ __forceinline__ bool pop(int &x) {
+        if (sp == 0)
+            return false;
+        x = v[--sp];
+        return true;
+    }
+};
+
+struct RegRay {
+    float o[3], d[3];
+    __device__ __forceinline__ float ox() const { return o[0]; }
+    __device__ __forceinline__ float oy() const { return o[1]; }
+    __device__ __forceinline__ float oz() const { return o[2]; }
+    __device__ __forceinline__ float dx() const { return d[0]; }
+    __device__ __forceinline__ float dy() const { return d[1]; }
+    __device__ __forceinline__ float dz() const { return d[2]; }
+};
+
 // Refines (tmin, idx) -- already holding the best of the brute-force list, or (1e20, 0) -- with the tree's spheres.
+// Plain per-lane loop: used by the first-hit diagnostic kernel and by the lock-step material kernel of small launches.
 __device__ __forceinline__ void bvh_nearest(const BvhScene &sc, float ox, float oy, float oz, float dx, float dy, float dz, float eps, float &tmin,
                                             int &idx) {
     if (sc.n_small <= 0)
@@ -70,40 +204,16 @@ __device__ __forceinline__ void bvh_nearest(const BvhScene &sc, float ox, float 
         bvh_leaf(sc, ~sc.only_leaf, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
         return;
     }
-    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
-    int stack[kBvhStack];
-    int sp = 0;
-    int node = 0;
-    for (;;) {
-        const BvhNode *nd = sc.nodes + node;
-        const float4 a = __ldg(&nd->a), b = __ldg(&nd->b), c = __ldg(&nd->c);
-        const int left = __ldg(&nd->left), right = __ldg(&nd->right);
-        float tl, tr;
-        bool hl = hit_box(ox, oy, oz, ix, iy, iz, a.x, a.y, a.z, a.w, b.x, b.y, tmin, tl);
-        bool hr = hit_box(ox, oy, oz, ix, iy, iz, b.z, b.w, c.x, c.y, c.z, c.w, tmin, tr);
-        if (hl && left < 0) {
-            bvh_leaf(sc, ~left, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
-            hl = false;
-        }
-        if (hr && right < 0) {
-            bvh_leaf(sc, ~right, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
-            hr = false;
-        }
-        if (hl && hr) {  // near child first, far child on the stack
-            const bool lfirst = tl <= tr;
-            if (sp < kBvhStack)
-                stack[sp++] = lfirst ? right : left;
-            node = lfirst ? left : right;
-        } else if (hl) {
-            node = left;
-        } else if (hr) {
-            node = right;
-        } else {
-            if (sp == 0)
-                break;
-            node = stack[--sp];
-        }
+    const BvhRay r = bvh_ray(sc, ox, oy, oz, dx, dy, dz);
+    if (r.far_origin) {
+        bvh_all_leaves(sc, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
+        return;
     }
+    RegRay ray = {{ox, oy, oz}, {dx, dy, dz}};
+    LocalStack st;
+    int node = 0;
+    while (node >= 0)
+        bvh_step(sc, r, ray, eps, node, tmin, idx, st);
 }
 
 }  // namespace ptb200

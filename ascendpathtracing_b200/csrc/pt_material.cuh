@@ -72,36 +72,8 @@ __device__ __forceinline__ void sincos2pi(float u, float &s_out, float &c_out) {
     c_out = (k == 0) ? c : (k == 1) ? -s : (k == 2) ? -c : s;
 }
 
-// One bounce.  Returns true when the path has ended (its radiance is final).
-// BVH = false: all spheres in the constant bank (nsph of them), per-sphere data from shared memory.
-// BVH = true : the constant bank holds only the huge spheres (nsph = their count, indices through bvh.big_index), the rest
-//              is found through the tree; per-sphere data comes from global memory by original index.
-template <int NS, bool BVH>
-__device__ __forceinline__ bool material_bounce(MatPath &p, int nsph, float one, float eps, int rr_start, unsigned long long seed,
-                                                unsigned long long path, const MatShared &sh, const BvhScene &bvh) {
-    PathState ray;
-    ray.ox = p.ox, ray.oy = p.oy, ray.oz = p.oz, ray.dx = p.dx, ray.dy = p.dy, ray.dz = p.dz;
-    float tmin;
-    int idx;
-    if (BVH) {
-        tmin = kMiss;
-        idx = 0;
-        if (nsph > 0) {
-            nearest_hit<0>(ray, nsph, one, eps, tmin, idx);
-            idx = (tmin < kMiss) ? __ldg(bvh.big_index + idx) : 0;
-        }
-        bvh_nearest(bvh, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, eps, tmin, idx);
-    } else {
-        nearest_hit<NS>(ray, nsph, one, eps, tmin, idx);
-    }
-    if (!(tmin < kMiss))
-        return true;
-    uint32_t w[4] = {static_cast<uint32_t>(path), static_cast<uint32_t>(path >> 32), static_cast<uint32_t>(p.depth), 0x4d41u};
-    philox4x32_10(w, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-    const float u1 = __fmul_rn(static_cast<float>(w[0] >> 8), 5.9604645e-8f), u2 = __fmul_rn(static_cast<float>(w[1] >> 8), 5.9604645e-8f);
-    const float u3 = __fmul_rn(static_cast<float>(w[2] >> 8), 5.9604645e-8f), u4 = __fmul_rn(static_cast<float>(w[3] >> 8), 5.9604645e-8f);
-
-    float4 ctr, col, emi;
+// Per-sphere data of the hit sphere: shared memory (constant-bank scenes) or global memory by original index (BVH scenes).
+template <bool BVH> __device__ __forceinline__ void fetch_hit_sphere(int idx, const MatShared &sh, const BvhScene &bvh, float4 &ctr, float4 &col, float4 &emi) {
     if (BVH) {
         const float4 g = __ldg(bvh.geom + idx), cm = __ldg(bvh.color + idx);
         ctr = make_float4(g.x, g.y, g.z, cm.w);
@@ -112,6 +84,21 @@ __device__ __forceinline__ bool material_bounce(MatPath &p, int nsph, float one,
         col = sh.color[idx];
         emi = sh.emission[idx];
     }
+}
+
+// Shading half of a bounce, given the nearest hit (tmin, idx).  Returns true when the path has ended (its radiance is final).
+template <bool BVH>
+__device__ __forceinline__ bool material_shade(MatPath &p, float tmin, int idx, int rr_start, unsigned long long seed, unsigned long long path,
+                                               const MatShared &sh, const BvhScene &bvh) {
+    if (!(tmin < kMiss))
+        return true;
+    uint32_t w[4] = {static_cast<uint32_t>(path), static_cast<uint32_t>(path >> 32), static_cast<uint32_t>(p.depth), 0x4d41u};
+    philox4x32_10(w, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const float u1 = __fmul_rn(static_cast<float>(w[0] >> 8), 5.9604645e-8f), u2 = __fmul_rn(static_cast<float>(w[1] >> 8), 5.9604645e-8f);
+    const float u3 = __fmul_rn(static_cast<float>(w[2] >> 8), 5.9604645e-8f), u4 = __fmul_rn(static_cast<float>(w[3] >> 8), 5.9604645e-8f);
+
+    float4 ctr, col, emi;
+    fetch_hit_sphere<BVH>(idx, sh, bvh, ctr, col, emi);
     const float xx = __fadd_rn(p.ox, __fmul_rn(p.dx, tmin)), xy = __fadd_rn(p.oy, __fmul_rn(p.dy, tmin)), xz = __fadd_rn(p.oz, __fmul_rn(p.dz, tmin));
     float nx = __fsub_rn(xx, ctr.x), ny = __fsub_rn(xy, ctr.y), nz = __fsub_rn(xz, ctr.z);
     normalize_rn(nx, ny, nz);
@@ -198,6 +185,19 @@ __device__ __forceinline__ bool material_bounce(MatPath &p, int nsph, float one,
     }
     p.ox = xx, p.oy = xy, p.oz = xz;
     return false;
+}
+
+// One bounce of the constant-bank kernel: nearest hit over the nsph spheres of the constant bank, then shading.
+template <int NS>
+__device__ __forceinline__ bool material_bounce(MatPath &p, int nsph, float one, float eps, int rr_start, unsigned long long seed,
+                                                unsigned long long path, const MatShared &sh) {
+    PathState ray;
+    ray.ox = p.ox, ray.oy = p.oy, ray.oz = p.oz, ray.dx = p.dx, ray.dy = p.dy, ray.dz = p.dz;
+    float tmin;
+    int idx;
+    nearest_hit<NS>(ray, nsph, one, eps, tmin, idx);
+    const BvhScene none = {};
+    return material_shade<false>(p, tmin, idx, rr_start, seed, path, sh, none);
 }
 
 }  // namespace ptb200

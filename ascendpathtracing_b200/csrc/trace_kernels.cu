@@ -229,25 +229,19 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
 }
 
 
-// ---- material extension kernel (pt_material.cuh) ------------------------------------------------------------------
+// ---- material extension kernel (pt_material.cuh), constant-bank scenes -----------------------------------------------
 // Same persistent warps, ring and ballot-ranked regeneration; one iteration = one bounce of material_bounce().
-template <int NS, bool BVH, bool GEN>
+template <int NS, bool GEN>
 __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                            int max_depth, int rr_start, int nsph, int stride, float eps, float one,
                                                                            unsigned long long seed, unsigned long long path0,
-                                                                           unsigned long long *__restrict__ stats, const BvhScene bvh,
-                                                                           unsigned long long *work_counter) {
+                                                                           unsigned long long *__restrict__ stats, unsigned long long *work_counter) {
     extern __shared__ float4 smem[];
     MatShared sh;
-    if (BVH) {
-        sh.center = sh.color = sh.emission = nullptr;  // per-sphere data comes from global memory
-        __syncthreads();
-    } else {
-        stage_materials_shared(smem, spheres, nsph, stride, sh);
-    }
+    stage_materials_shared(smem, spheres, nsph, stride, sh);
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    PathFeeder<GEN> feed(pl, reinterpret_cast<float *>(smem + (BVH ? 0 : 3 * nsph)) + warp_in_block * (6 * kRing), work_counter, count, lane);
+    PathFeeder<GEN> feed(pl, reinterpret_cast<float *>(smem + 3 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
 
     MatPath p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -287,9 +281,271 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
         }
         if (active) {  // dead lanes of a finished range idle; live ones diverge by material inside
             segs++;
-            const bool ended = material_bounce<NS, BVH>(p, nsph, one, eps, rr_start, seed, path0 + mine, sh, bvh);
+            const bool ended = material_bounce<NS>(p, nsph, one, eps, rr_start, seed, path0 + mine, sh);
             want = ended || p.depth >= max_depth;
         }
+    }
+    if (stats != nullptr) {
+        unsigned int w = segs;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (lane == 0)
+            atomicAdd(stats, static_cast<unsigned long long>(w));
+    }
+}
+
+// ---- material extension kernel, BVH scenes: warp-local wavefront -------------------------------------------------------
+// A tree walk takes 28 steps on average in the C4 scene but ten times that for the unluckiest ray of a warp, so a warp
+// that walks 32 rays in lock step and shades them together keeps 3 of its 32 lanes busy (ncu, profiles/r2_c4_v1_*).
+// Here lanes are decoupled from paths.  Each warp owns a pool of kPool path slots in shared memory and two queues of slot
+// numbers: rays waiting for a tree walk (tq) and hits waiting for shading (sq).  A lane takes any waiting ray, walks the
+// tree, drops the hit into sq and takes the next ray; when 32 hits have gathered the whole warp shades them at once
+// (materials, Russian roulette, regeneration of ended paths, the brute-force pass over the huge spheres) and the
+// continuing rays go back to tq.  With kPool = 64 every lane always finds a ray while work lasts: 32 rays in flight, the
+// other 32 slots split between the two queues, and shading runs exactly when tq is empty.
+// Queue traffic is batched: the walk loop runs until kRefillLanes lanes have finished before the warp stops to requeue.
+constexpr int kPool = 64;
+constexpr int kShortStack = 12;  // stack entries per lane in shared memory; deeper ones overflow to local memory
+#ifndef PTB_REFILL_LANES
+#define PTB_REFILL_LANES 8
+#endif
+constexpr int kRefillLanes = PTB_REFILL_LANES;
+
+struct WarpPool {
+    float ray[6][kPool];  // ox oy oz dx dy dz
+    float thr[3][kPool];  // throughput
+    float rad[3][kPool];  // radiance gathered so far
+    int depth[kPool];     // < 0: slot holds no path yet
+    unsigned int path[kPool];
+    float tmin[kPool];    // best hit so far (brute-force list, then the tree)
+    int idx[kPool];
+    unsigned char tq[kPool], sq[kPool];
+};
+
+struct HybridStack {
+    int *s;  // this lane's column in shared memory: entry k at s[k * kTraceThreads]
+    int ovf[kBvhStack - kShortStack];
+    int sp;
+    __device__ __forceinline__ void push(int x) {
+        if (sp < kShortStack)
+            s[sp * kTraceThreads] = x;
+        else
+            ovf[sp - kShortStack] = x;
+        sp++;
+    }
+    __device__ __forceinline__ bool pop(int &x) {
+        if (sp == 0)
+            return false;
+        sp--;
+        x = sp < kShortStack ? s[sp * kTraceThreads] : ovf[sp - kShortStack];
+        return true;
+    }
+};
+
+struct PoolRay {
+    const WarpPool *pool;
+    int slot;
+    __device__ __forceinline__ float ox() const { return pool->ray[0][slot]; }
+    __device__ __forceinline__ float oy() const { return pool->ray[1][slot]; }
+    __device__ __forceinline__ float oz() const { return pool->ray[2][slot]; }
+    __device__ __forceinline__ float dx() const { return pool->ray[3][slot]; }
+    __device__ __forceinline__ float dy() const { return pool->ray[4][slot]; }
+    __device__ __forceinline__ float dz() const { return pool->ray[5][slot]; }
+};
+
+static __device__ __noinline__ void generate_ray_to_pool(unsigned int path, float *slot) {
+    float r[6];
+    generate_ray(c_gen, static_cast<long long>(path), r);
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+        slot[c * kPool] = r[c];
+}
+
+#ifndef PTB_BVH_BLOCKS_PER_SM
+#define PTB_BVH_BLOCKS_PER_SM 3
+#endif
+template <bool GEN>
+__global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
+    trace_materials_bvh_kernel(const TracePlanes pl, unsigned int count, int max_depth, int rr_start, int nbig, float eps, float one,
+                               unsigned long long seed, unsigned long long path0, unsigned long long *__restrict__ stats, const BvhScene bvh,
+                               unsigned long long *work_counter, unsigned int chunk) {
+    extern __shared__ float4 smem[];
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int warp_in_block = threadIdx.x >> 5;
+    unsigned int lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    WarpPool &pool = reinterpret_cast<WarpPool *>(smem)[warp_in_block];
+    const MatShared nosh = {nullptr, nullptr, nullptr};
+
+    // every slot starts in the shading queue as "no path yet": the first two shading rounds just fetch paths
+    pool.depth[lane] = -1, pool.depth[lane + 32] = -1;
+    pool.sq[lane] = static_cast<unsigned char>(lane), pool.sq[lane + 32] = static_cast<unsigned char>(lane + 32);
+    int sq_count = kPool, tq_count = 0;
+    unsigned int next = 0, chunk_end = 0;  // the warp's current chunk of paths: [next, chunk_end)
+    __syncwarp();
+
+    bool cur = false;  // this lane holds a ray (walking, or finished and not yet deposited)
+    int slot = 0, node = -1, idx = 0;
+    float tmin = kMiss;
+    BvhRay r = {};
+    HybridStack st;
+    st.s = reinterpret_cast<int *>(reinterpret_cast<WarpPool *>(smem) + kWarpsPerBlock) + threadIdx.x;
+    st.sp = 0;
+    unsigned int segs = 0;
+
+    for (;;) {
+        // 1. lanes whose walk ended deposit their hit
+        const bool fin = cur && node < 0;
+        const unsigned int fmask = __ballot_sync(0xffffffffu, fin);
+        if (fmask != 0u) {
+            if (fin) {
+                pool.tmin[slot] = tmin;
+                pool.idx[slot] = idx;
+                pool.sq[sq_count + __popc(fmask & lt)] = static_cast<unsigned char>(slot);
+                cur = false;
+            }
+            sq_count += __popc(fmask);
+            __syncwarp();
+        }
+        const unsigned int busy = __ballot_sync(0xffffffffu, cur);
+        // 2. a full warp of hits (or the last few): shade, regenerate, brute-force pass, back to tq
+        if (sq_count >= 32 || (sq_count > 0 && busy == 0u && tq_count == 0)) {
+            const int n_take = sq_count < 32 ? sq_count : 32;
+            const bool has = static_cast<int>(lane) < n_take;
+            int s2 = 0;
+            if (has)
+                s2 = pool.sq[sq_count - n_take + lane];
+            sq_count -= n_take;
+            MatPath p;
+            p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
+            p.dz = 1.0f;
+            p.tr = p.tg = p.tb = 1.0f;
+            p.lr = p.lg = p.lb = 0.0f;
+            p.depth = 0;
+            unsigned int mypath = 0;
+            bool ended = true;
+            if (has && pool.depth[s2] >= 0) {
+                p.ox = pool.ray[0][s2], p.oy = pool.ray[1][s2], p.oz = pool.ray[2][s2];
+                p.dx = pool.ray[3][s2], p.dy = pool.ray[4][s2], p.dz = pool.ray[5][s2];
+                p.tr = pool.thr[0][s2], p.tg = pool.thr[1][s2], p.tb = pool.thr[2][s2];
+                p.lr = pool.rad[0][s2], p.lg = pool.rad[1][s2], p.lb = pool.rad[2][s2];
+                p.depth = pool.depth[s2];
+                mypath = pool.path[s2];
+                segs++;
+                ended = material_shade<true>(p, pool.tmin[s2], pool.idx[s2], rr_start, seed, path0 + mypath, nosh, bvh) || p.depth >= max_depth;
+                if (ended) {
+                    pl.col[0][mypath] = p.lr;
+                    pl.col[1][mypath] = p.lg;
+                    pl.col[2][mypath] = p.lb;
+                }
+            }
+            // ended paths are replaced by the next consecutive paths of the warp's chunk (ballot-ranked)
+            const bool need = has && ended;
+            const unsigned int nmask = __ballot_sync(0xffffffffu, need);
+            bool got = false;
+            if (nmask != 0u) {
+                const unsigned int n_need = __popc(nmask), rank = __popc(nmask & lt);
+                const unsigned int avail = chunk_end - next;
+                unsigned int fresh = count, fresh_end = count;
+                if (n_need > avail) {  // warp-uniform: claim the next chunk
+                    unsigned long long base = 0;
+                    if (lane == 0)
+                        base = atomicAdd(work_counter, static_cast<unsigned long long>(chunk));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    fresh = base < count ? static_cast<unsigned int>(base) : count;
+                    fresh_end = (count - fresh < chunk) ? count : fresh + chunk;
+                }
+                const unsigned int path = rank < avail ? next + rank : fresh + (rank - avail);
+                got = need && (rank < avail || path < fresh_end);
+                if (n_need > avail) {
+                    next = fresh + (n_need - avail);
+                    chunk_end = fresh_end;
+                    if (next > chunk_end)
+                        next = chunk_end;
+                } else {
+                    next += n_need;
+                }
+                if (got) {
+                    if (GEN) {
+                        generate_ray_to_pool(path, &pool.ray[0][s2]);
+                        p.ox = pool.ray[0][s2], p.oy = pool.ray[1][s2], p.oz = pool.ray[2][s2];
+                        p.dx = pool.ray[3][s2], p.dy = pool.ray[4][s2], p.dz = pool.ray[5][s2];
+                    } else {
+                        p.ox = pl.ray[0][path], p.oy = pl.ray[1][path], p.oz = pl.ray[2][path];
+                        p.dx = pl.ray[3][path], p.dy = pl.ray[4][path], p.dz = pl.ray[5][path];
+                    }
+                    p.tr = p.tg = p.tb = 1.0f;
+                    p.lr = p.lg = p.lb = 0.0f;
+                    p.depth = 0;
+                    mypath = path;
+                }
+            }
+            const bool cont = has && (!ended || got);
+            if (cont) {  // all lanes except at the very end of the launch
+                float t = kMiss;
+                int i = 0;
+                if (nbig > 0) {
+                    PathState ray;
+                    ray.ox = p.ox, ray.oy = p.oy, ray.oz = p.oz, ray.dx = p.dx, ray.dy = p.dy, ray.dz = p.dz;
+                    nearest_hit<0>(ray, nbig, one, eps, t, i);
+                    i = (t < kMiss) ? __ldg(bvh.big_index + i) : 0;
+                }
+                pool.ray[0][s2] = p.ox, pool.ray[1][s2] = p.oy, pool.ray[2][s2] = p.oz;
+                pool.ray[3][s2] = p.dx, pool.ray[4][s2] = p.dy, pool.ray[5][s2] = p.dz;
+                pool.thr[0][s2] = p.tr, pool.thr[1][s2] = p.tg, pool.thr[2][s2] = p.tb;
+                pool.rad[0][s2] = p.lr, pool.rad[1][s2] = p.lg, pool.rad[2][s2] = p.lb;
+                pool.depth[s2] = p.depth;
+                pool.path[s2] = mypath;
+                pool.tmin[s2] = t;
+                pool.idx[s2] = i;
+            }
+            const unsigned int cmask = __ballot_sync(0xffffffffu, cont);
+            if (cont)
+                pool.tq[tq_count + __popc(cmask & lt)] = static_cast<unsigned char>(s2);
+            tq_count += __popc(cmask);
+            __syncwarp();
+        }
+        // 3. idle lanes take waiting rays
+        if (tq_count > 0 && busy != 0xffffffffu) {
+            const unsigned int imask = ~busy;
+            const int rank = __popc(imask & lt);
+            if (!cur && rank < tq_count) {
+                slot = pool.tq[tq_count - 1 - rank];
+                const float ox = pool.ray[0][slot], oy = pool.ray[1][slot], oz = pool.ray[2][slot];
+                const float dx = pool.ray[3][slot], dy = pool.ray[4][slot], dz = pool.ray[5][slot];
+                tmin = pool.tmin[slot];
+                idx = pool.idx[slot];
+                cur = true;
+                node = -1;
+                st.sp = 0;
+                if (bvh.n_small == 1) {
+                    bvh_leaf(bvh, ~bvh.only_leaf, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
+                } else if (bvh.n_small > 1) {
+                    r = bvh_ray(bvh, ox, oy, oz, dx, dy, dz);
+                    if (r.far_origin)
+                        bvh_all_leaves(bvh, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
+                    else
+                        node = 0;
+                }
+            }
+            const int taken = __popc(imask);
+            tq_count -= taken < tq_count ? taken : tq_count;
+            __syncwarp();
+        }
+        // 4. walk until kRefillLanes more lanes have finished (or nobody walks any more)
+        const unsigned int act = __ballot_sync(0xffffffffu, cur && node >= 0);
+        if (act == 0u) {
+            if (__ballot_sync(0xffffffffu, cur) == 0u && sq_count == 0 && tq_count == 0)
+                break;
+            continue;
+        }
+        const int stop_at = __popc(act) > kRefillLanes ? __popc(act) - kRefillLanes : 0;
+        const PoolRay pray = {&pool, slot};
+        do {
+            if (cur && node >= 0)
+                bvh_step(bvh, r, pray, eps, node, tmin, idx, st);
+        } while (__popc(__ballot_sync(0xffffffffu, cur && node >= 0)) > stop_at);
     }
     if (stats != nullptr) {
         unsigned int w = segs;
@@ -477,13 +733,14 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
             return e;
     }
     const bool use_tree = tree != nullptr;
-    const size_t smem = (use_tree ? 0 : sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count)) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
+    const size_t smem = use_tree ? sizeof(WarpPool) * kWarpsPerBlock + sizeof(int) * kShortStack * kTraceThreads
+                                 : sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
     const bool ten = !use_tree && (p.sphere_count == 9 || p.sphere_count == 10);  // smallpt's scene: unrolled pairs (index 9 is padding)
     int occ = 0;
     // the fused-generation variants have the same resource footprint as the SoA ones (the generator is an out-of-line call)
-    if ((e = use_tree ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, true, false>, kTraceThreads, smem)
-              : ten   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<10, false, false>, kTraceThreads, smem)
-                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, false, false>, kTraceThreads, smem)) != cudaSuccess)
+    if ((e = use_tree ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_bvh_kernel<false>, kTraceThreads, smem)
+              : ten   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<10, false>, kTraceThreads, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, false>, kTraceThreads, smem)) != cudaSuccess)
         return e;
     if (occ < 1)
         occ = 1;
@@ -496,7 +753,9 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
             pl.ray[c] = rays + c * n + a;
         for (int c = 0; c < 3; c++)
             pl.col[c] = colors + c * n + a;
-        const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
+        // the wavefront kernel keeps kPool paths per warp in flight, the lock-step kernels one per lane
+        const int64_t per_block = use_tree ? static_cast<int64_t>(kPool) * kWarpsPerBlock : kTraceThreads;
+        const int64_t need = (m + per_block - 1) / per_block;
         const int grid = static_cast<int>(need < cap ? need : cap);
         if ((e = cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned long long), stream)) != cudaSuccess)
             return e;
@@ -507,16 +766,27 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
             if ((e = stage_gen(stream, make_raygen_source_shifted(*gen, a - first, m))) != cudaSuccess)
                 return e;
         }
-#define PTB_LAUNCH_MAT(NSV, BVHV, GENV)                                                                                                        \
-    trace_materials_kernel<NSV, BVHV, GENV><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,     \
-                                                                                   p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh, \
-                                                                                   s->work_counter)
+#define PTB_LAUNCH_MAT(NSV, GENV)                                                                                                            \
+    trace_materials_kernel<NSV, GENV><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,          \
+                                                                             p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats,        \
+                                                                             s->work_counter)
         if (use_tree) {
-            if (gen) PTB_LAUNCH_MAT(0, true, true); else PTB_LAUNCH_MAT(0, true, false);
+            // chunks of consecutive paths per warp claim: about 8 claims per warp over the launch, 32..2048 paths each
+            int64_t chunk = m / (static_cast<int64_t>(grid) * kWarpsPerBlock * 8);
+            chunk = (chunk + 31) / 32 * 32;
+            chunk = chunk < 32 ? 32 : (chunk > 2048 ? 2048 : chunk);
+            if (gen)
+                trace_materials_bvh_kernel<true><<<grid, kTraceThreads, smem, stream>>>(pl, mm, mp.max_depth, mp.rr_start, p.sphere_count,
+                                                                                      mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh, s->work_counter,
+                                                                                      static_cast<unsigned int>(chunk));
+            else
+                trace_materials_bvh_kernel<false><<<grid, kTraceThreads, smem, stream>>>(pl, mm, mp.max_depth, mp.rr_start, p.sphere_count,
+                                                                                       mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh, s->work_counter,
+                                                                                       static_cast<unsigned int>(chunk));
         } else if (ten) {
-            if (gen) PTB_LAUNCH_MAT(10, false, true); else PTB_LAUNCH_MAT(10, false, false);
+            if (gen) PTB_LAUNCH_MAT(10, true); else PTB_LAUNCH_MAT(10, false);
         } else {
-            if (gen) PTB_LAUNCH_MAT(0, false, true); else PTB_LAUNCH_MAT(0, false, false);
+            if (gen) PTB_LAUNCH_MAT(0, true); else PTB_LAUNCH_MAT(0, false);
         }
 #undef PTB_LAUNCH_MAT
         if ((e = cudaGetLastError()) != cudaSuccess)
