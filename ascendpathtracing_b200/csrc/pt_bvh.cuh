@@ -12,7 +12,7 @@
 //
 // What bounds traversal on B200 (ncu, profiles/r2_c4_*): incoherent rays make every node fetch touch one cache line per
 // lane, and L1 looks up one line per clock per SM -- the tag stage, not the arithmetic, is the limit.  So a node is
-// 32 bytes = two LDG.128 (one per child: 6 x 16-bit box planes + reference), half the lines of the float layout:
+// 32 bytes = ONE LDG.256 (per child: 6 x 16-bit box planes + reference), a quarter of the float layout's lookups:
 //   * planes are quantised to a 16-bit grid over the tree's bounds, rounded outwards and grown by kGridGrow units;
 //   * decoding costs nothing: PRMT drops the 16 bits into the mantissa of 2^23 (0x4B000000 | q = 2^23 + q exactly), and
 //     the slab distance is ONE FFMA, t = (2^23 + q) * id + c with id = 1 / (d * scale) and c = -(2^23 + round(og)) * id
@@ -24,7 +24,7 @@
 // Origins further than 2^21 grid units from the tree (64 scene widths) fall back to an exact loop over all spheres.
 //
 // Layout: LBVH (Morton order, Karras 2012); a reference < 0 is a leaf (~ref = sphere).  Traversal: near child first,
-// leaves tested inline (at most two per step, one code copy), stack policy supplied by the caller.
+// leaf tests and stack policy supplied by the caller.
 #pragma once
 #include "pt_device.cuh"
 
@@ -103,6 +103,13 @@ __device__ __forceinline__ bool hit_qbox(const BvhRay &r, unsigned int wx, unsig
     return tf >= fmaxf(tn, 0.0f) && tn <= tbest;
 }
 
+// The whole 32-byte node in ONE 256-bit load (LDG.E.256, new on sm_100): one L1 tag lookup per lane per step.
+__device__ __forceinline__ void ldg_node(const QNode *n, uint4 &L, uint4 &R) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(L.x), "=r"(L.y), "=r"(L.z), "=r"(L.w), "=r"(R.x), "=r"(R.y), "=r"(R.z), "=r"(R.w)
+        : "l"(n));
+}
+
 // Exact leaf test (sphere_t's arithmetic, rt_helper.h:255-370) with the reference's (t, index) merge: smaller t, then
 // lower index.  A negative or NaN discriminant is a miss (sqrt gives NaN, both compares fail, t = 1e20) and a miss can
 // never replace the current best, so the square root is skipped for it.
@@ -128,41 +135,44 @@ __device__ __forceinline__ void bvh_leaf(const BvhScene &sc, int sphere, float o
     }
 }
 
-// One traversal step at internal node `node`: tests both children, runs the exact test on hit leaves, and leaves the next
-// internal node in `node` (or -1 when the stack ran empty: traversal finished).
-// Stack: push(int), bool pop(int&).  Ray: ox(), oy(), ... accessors of the exact ray for the leaf tests.
+// One traversal step at internal node `node`: tests both child boxes, reports hit leaves in leaf_a / leaf_b (sphere index
+// or -1; leaf_b is only set when leaf_a is) and leaves the next internal node in `node` (-1 when the stack ran empty:
+// traversal finished).  The caller runs the exact test on the leaves -- at once, or batched across the warp.
+// Stack: push_if(bool, int), int pop_if(bool, int fallback) -- predicated, no branches on the common path.
+template <class Stack>
+__device__ __forceinline__ void bvh_step_boxes(const BvhScene &sc, const BvhRay &r, float tmin, int &node, int &leaf_a, int &leaf_b, Stack &st) {
+    uint4 L, R;
+    ldg_node(sc.qnodes + node, L, R);
+    const int left = static_cast<int>(L.w), right = static_cast<int>(R.w);
+#ifdef PTB_BVH_PREFETCH  // both children towards L1 while this node's boxes are tested
+    if (left >= 0)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.qnodes + left));
+    if (right >= 0)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.qnodes + right));
+#endif
+    float tl, tr;
+    const bool bl = hit_qbox(r, L.x, L.y, L.z, tmin, tl);
+    const bool br = hit_qbox(r, R.x, R.y, R.z, tmin, tr);
+    const bool ll = bl && left < 0, lr = br && right < 0;
+    leaf_a = ll ? ~left : (lr ? ~right : -1);
+    leaf_b = (ll && lr) ? ~right : -1;
+    const bool hl = bl && left >= 0, hr = br && right >= 0;
+    // near child first, far child on the stack; nothing hit: pop
+    const bool lfirst = tl <= tr, both = hl && hr;
+    st.push_if(both, lfirst ? right : left);
+    const int next = both ? (lfirst ? left : right) : (hl ? left : right);
+    node = st.pop_if(!(hl || hr), next);
+}
+
+// Step with the leaves tested at once (the plain per-lane walk).
 template <class Stack, class Ray>
 __device__ __forceinline__ void bvh_step(const BvhScene &sc, const BvhRay &r, const Ray &ray, float eps, int &node, float &tmin, int &idx, Stack &st) {
-    const uint4 *q = reinterpret_cast<const uint4 *>(sc.qnodes + node);
-    const uint4 L = __ldg(q), R = __ldg(q + 1);
-    const int left = static_cast<int>(L.w), right = static_cast<int>(R.w);
-    float tl, tr;
-    bool hl = hit_qbox(r, L.x, L.y, L.z, tmin, tl);
-    bool hr = hit_qbox(r, R.x, R.y, R.z, tmin, tr);
-    int leaf_a = (hl && left < 0) ? ~left : -1;
-    int leaf_b = (hr && right < 0) ? ~right : -1;
-    hl = hl && left >= 0;
-    hr = hr && right >= 0;
-    if (leaf_a < 0) {
-        leaf_a = leaf_b;
-        leaf_b = -1;
-    }
-    while (leaf_a >= 0) {  // at most two rounds; one copy of the leaf code for the warp to share
+    int leaf_a, leaf_b;
+    bvh_step_boxes(sc, r, tmin, node, leaf_a, leaf_b, st);
+    if (leaf_a >= 0)
         bvh_leaf(sc, leaf_a, ray.ox(), ray.oy(), ray.oz(), ray.dx(), ray.dy(), ray.dz(), eps, tmin, idx);
-        leaf_a = leaf_b;
-        leaf_b = -1;
-    }
-    if (hl && hr) {  // near child first, far child on the stack
-        const bool lfirst = tl <= tr;
-        st.push(lfirst ? right : left);
-        node = lfirst ? left : right;
-    } else if (hl) {
-        node = left;
-    } else if (hr) {
-        node = right;
-    } else if (!st.pop(node)) {
-        node = -1;
-    }
+    if (leaf_b >= 0)
+        bvh_leaf(sc, leaf_b, ray.ox(), ray.oy(), ray.oz(), ray.dx(), ray.dy(), ray.dz(), eps, tmin, idx);
 }
 
 // Exact fallback for rays the quantised traversal does not cover: every sphere of the tree, ascending index.
@@ -173,14 +183,16 @@ static __device__ __noinline__ void bvh_all_leaves(const BvhScene &sc, float ox,
 }
 
 struct LocalStack {  // per-lane stack in local memory
-    int v[kBvhStack];
-    int sp = 0;
-    __device__ __forceinline__ void push(int x) { v[sp++] = x; }
-    __device__ __forceinline__ bool pop(int &x) {
-        if (sp == 0)
-            return false;
-        x = v[--sp];
-        return true;
+    int *v;
+    int sp;
+    __device__ __forceinline__ void push_if(bool c, int x) {
+        if (c)
+            v[sp++] = x;
+    }
+    __device__ __forceinline__ int pop_if(bool c, int fallback) {
+        if (!c)
+            return fallback;
+        return sp == 0 ? -1 : v[--sp];
     }
 };
 
@@ -210,7 +222,8 @@ __device__ __forceinline__ void bvh_nearest(const BvhScene &sc, float ox, float 
         return;
     }
     RegRay ray = {{ox, oy, oz}, {dx, dy, dz}};
-    LocalStack st;
+    int stack_mem[kBvhStack];
+    LocalStack st = {stack_mem, 0};
     int node = 0;
     while (node >= 0)
         bvh_step(sc, r, ray, eps, node, tmin, idx, st);

@@ -311,6 +311,10 @@ constexpr int kShortStack = 12;  // stack entries per lane in shared memory; dee
 #define PTB_REFILL_LANES 8
 #endif
 constexpr int kRefillLanes = PTB_REFILL_LANES;
+#ifndef PTB_LEAF_BATCH
+#define PTB_LEAF_BATCH 4
+#endif
+constexpr int kLeafBatch = PTB_LEAF_BATCH;
 
 struct WarpPool {
     float ray[6][kPool];  // ox oy oz dx dy dz
@@ -324,22 +328,26 @@ struct WarpPool {
 };
 
 struct HybridStack {
-    int *s;  // this lane's column in shared memory: entry k at s[k * kTraceThreads]
-    int ovf[kBvhStack - kShortStack];
+    int *s;    // this lane's column in shared memory: entry k at s[k * kTraceThreads]
+    int *ovf;  // local memory, entries kShortStack and up (deep, unbalanced trees only)
     int sp;
-    __device__ __forceinline__ void push(int x) {
-        if (sp < kShortStack)
+    __device__ __forceinline__ void push_if(bool c, int x) {
+        const bool fast = c && sp < kShortStack;
+        if (fast)
             s[sp * kTraceThreads] = x;
-        else
+        if (c && !fast)
             ovf[sp - kShortStack] = x;
-        sp++;
+        sp += c ? 1 : 0;
     }
-    __device__ __forceinline__ bool pop(int &x) {
-        if (sp == 0)
-            return false;
-        sp--;
-        x = sp < kShortStack ? s[sp * kTraceThreads] : ovf[sp - kShortStack];
-        return true;
+    __device__ __forceinline__ int pop_if(bool c, int fallback) {
+        const bool have = c && sp > 0;
+        sp -= have ? 1 : 0;
+        int v = c ? -1 : fallback;
+        if (have && sp < kShortStack)
+            v = s[sp * kTraceThreads];
+        if (have && sp >= kShortStack)
+            v = ovf[sp - kShortStack];
+        return v;
     }
 };
 
@@ -363,7 +371,7 @@ static __device__ __noinline__ void generate_ray_to_pool(unsigned int path, floa
 }
 
 #ifndef PTB_BVH_BLOCKS_PER_SM
-#define PTB_BVH_BLOCKS_PER_SM 3
+#define PTB_BVH_BLOCKS_PER_SM 4
 #endif
 template <bool GEN>
 __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
@@ -387,15 +395,20 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
 
     bool cur = false;  // this lane holds a ray (walking, or finished and not yet deposited)
     int slot = 0, node = -1, idx = 0;
+    int pend = -1;     // a hit leaf whose exact test waits for company (kLeafBatch lanes) or for the next requeue stop
     float tmin = kMiss;
     BvhRay r = {};
-    HybridStack st;
-    st.s = reinterpret_cast<int *>(reinterpret_cast<WarpPool *>(smem) + kWarpsPerBlock) + threadIdx.x;
-    st.sp = 0;
+    int stack_overflow[kBvhStack - kShortStack];
+    HybridStack st = {reinterpret_cast<int *>(reinterpret_cast<WarpPool *>(smem) + kWarpsPerBlock) + threadIdx.x, stack_overflow, 0};
     unsigned int segs = 0;
 
     for (;;) {
-        // 1. lanes whose walk ended deposit their hit
+        // 1. leaf tests still pending, then lanes whose walk ended deposit their hit
+        if (pend >= 0) {
+            bvh_leaf(bvh, pend, pool.ray[0][slot], pool.ray[1][slot], pool.ray[2][slot], pool.ray[3][slot], pool.ray[4][slot], pool.ray[5][slot], eps,
+                     tmin, idx);
+            pend = -1;
+        }
         const bool fin = cur && node < 0;
         const unsigned int fmask = __ballot_sync(0xffffffffu, fin);
         if (fmask != 0u) {
@@ -543,8 +556,23 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
         const int stop_at = __popc(act) > kRefillLanes ? __popc(act) - kRefillLanes : 0;
         const PoolRay pray = {&pool, slot};
         do {
+            int leaf_a = -1, leaf_b = -1;
             if (cur && node >= 0)
-                bvh_step(bvh, r, pray, eps, node, tmin, idx, st);
+                bvh_step_boxes(bvh, r, tmin, node, leaf_a, leaf_b, st);
+            // Exact leaf tests are rare per lane (0.7 per ray) but a warp of 28 walkers meets one every other step, and run
+            // at once each costs the whole warp ~30 instructions and a memory round trip for one lane's benefit.  So a hit
+            // leaf waits in `pend` until kLeafBatch lanes have one (or the walk loop stops); the lane walks on with its
+            // old tmin meanwhile, which only culls less.  A lane that already holds one tests the older at once.
+            if (leaf_b >= 0)
+                bvh_leaf(bvh, leaf_b, pray.ox(), pray.oy(), pray.oz(), pray.dx(), pray.dy(), pray.dz(), eps, tmin, idx);
+            if (leaf_a >= 0 && pend >= 0)
+                bvh_leaf(bvh, pend, pray.ox(), pray.oy(), pray.oz(), pray.dx(), pray.dy(), pray.dz(), eps, tmin, idx);
+            pend = leaf_a >= 0 ? leaf_a : pend;
+            if (__popc(__ballot_sync(0xffffffffu, pend >= 0)) >= kLeafBatch) {
+                if (pend >= 0)
+                    bvh_leaf(bvh, pend, pray.ox(), pray.oy(), pray.oz(), pray.dx(), pray.dy(), pray.dz(), eps, tmin, idx);
+                pend = -1;
+            }
         } while (__popc(__ballot_sync(0xffffffffu, cur && node >= 0)) > stop_at);
     }
     if (stats != nullptr) {
