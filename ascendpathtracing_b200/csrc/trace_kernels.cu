@@ -63,9 +63,16 @@ constexpr int kRingBatches = 4;                  // batches of 32 rays in the ri
 constexpr int kRing = 32 * kRingBatches;         // ring entries per warp
 constexpr int kWarpsPerBlock = kTraceThreads / 32;
 
-constexpr int kChunkBatches = 64;  // a warp claims 64 batches = 2048 consecutive paths at a time
+// A warp claims this many batches of 32 consecutive paths at a time (>= kRingBatches).  The last chunk a warp claims is
+// the kernel's tail: with 64 batches (2048 paths) the trace kernel spent 5 % of its 2.1 ms, and the depth-50 sweep 10 %,
+// waiting for the unluckiest warps; 8 batches cost one atomic per 256 paths and measure within 0.5 % of the best
+// (tools/ab_chunks.sh, profiles/r1_chunk_size_ab.md).
+#ifndef PTB_CHUNK_BATCHES
+#define PTB_CHUNK_BATCHES 8
+#endif
+constexpr int kChunkBatches = PTB_CHUNK_BATCHES;
 
-// Streams paths to one warp: chunks of 2048 consecutive paths are claimed from a global counter (dynamic balancing:
+// Streams paths to one warp: chunks of 32 * kChunkBatches consecutive paths are claimed from a global counter (dynamic balancing:
 // with a static split the slowest warp set the kernel's duration and a third of the warp slots sat idle at the end),
 // fetched by coalesced cp.async batches of 32 rays into a shared-memory ring kRingBatches batches ahead of use, and
 // handed to the lanes that ask for a path in ballot-rank order, i.e. consecutive indices to the lanes of one swap.
@@ -370,6 +377,9 @@ static __device__ __noinline__ void generate_ray_to_pool(unsigned int path, floa
         slot[c * kPool] = r[c];
 }
 
+#ifndef PTB_BVH_MAX_CHUNK
+#define PTB_BVH_MAX_CHUNK 64
+#endif
 #ifndef PTB_BVH_BLOCKS_PER_SM
 #define PTB_BVH_BLOCKS_PER_SM 4
 #endif
@@ -799,10 +809,11 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
                                                                              p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats,        \
                                                                              s->work_counter)
         if (use_tree) {
-            // chunks of consecutive paths per warp claim: about 8 claims per warp over the launch, 32..2048 paths each
+            // chunks of consecutive paths per warp claim: 32..64 paths (one or two shading rounds); small, because the last
+            // chunk of the unluckiest warp is the kernel's tail and a path here can run to 64 bounces
             int64_t chunk = m / (static_cast<int64_t>(grid) * kWarpsPerBlock * 8);
             chunk = (chunk + 31) / 32 * 32;
-            chunk = chunk < 32 ? 32 : (chunk > 2048 ? 2048 : chunk);
+            chunk = chunk < 32 ? 32 : (chunk > PTB_BVH_MAX_CHUNK ? PTB_BVH_MAX_CHUNK : chunk);
             if (gen)
                 trace_materials_bvh_kernel<true><<<grid, kTraceThreads, smem, stream>>>(pl, mm, mp.max_depth, mp.rr_start, p.sphere_count,
                                                                                       mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh, s->work_counter,

@@ -56,6 +56,65 @@ def test_two_rank_stripes_assemble_to_the_single_rank_frame(tmp_path, oracle, w,
     assert np.array_equal(frame, whole)
 
 
+def _worker_interleaved(rank, world, port, w, h, parts, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from ascendpathtracing_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # pixel (y, x) carries its own coordinates, so the assembled frame is checkable without rendering anything
+        pieces = sharding.interleaved_stripes(w, rank, world, parts)
+        cols = [x for a, b in pieces for x in range(a, b)]
+        local = np.zeros((h, len(cols), 3), np.uint8)
+        for k, x in enumerate(cols):
+            local[:, k, 0] = x % 251
+            local[:, k, 1] = np.arange(h) % 251
+            local[:, k, 2] = rank
+        frame = sharding.gather_interleaved(torch.from_numpy(local), w, parts)
+        if rank == 0:
+            np.save(os.path.join(outdir, "frame.npy"), frame.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("w,h,parts", [(37, 4, 3), (5, 3, 4), (64, 2, 1)])
+def test_two_rank_interleaved_stripes_assemble(tmp_path, w, h, parts):
+    import torch.multiprocessing as mp
+
+    from ascendpathtracing_b200 import sharding
+    port = _free_port()
+    mp.spawn(_worker_interleaved, args=(2, port, w, h, parts, str(tmp_path)), nprocs=2, join=True)
+    frame = np.load(tmp_path / "frame.npy")
+    assert np.array_equal(frame[:, :, 0], np.broadcast_to(np.arange(w) % 251, (h, w)))
+    assert np.array_equal(frame[:, :, 1], np.broadcast_to((np.arange(h) % 251)[:, None], (h, w)))
+    owner = np.empty(w, np.uint8)
+    for r in range(2):
+        for a, b in sharding.interleaved_stripes(w, r, 2, parts):
+            owner[a:b] = r
+    assert np.array_equal(frame[0, :, 2], owner)
+
+
+def test_interleaved_partition_properties():
+    from ascendpathtracing_b200 import sharding
+    for width in (1, 7, 64, 1920, 3840):
+        for world in (1, 2, 8):
+            for parts in (1, 2, 4, 7):
+                seen = np.zeros(width, int)
+                for r in range(world):
+                    pieces = sharding.interleaved_stripes(width, r, world, parts)
+                    assert len(pieces) == parts
+                    assert all(a[1] <= b[0] for a, b in zip(pieces, pieces[1:]))
+                    for a, b in pieces:
+                        seen[a:b] += 1
+                assert (seen == 1).all()
+    assert sharding.interleaved_stripes(100, 1, 4, 1) == [sharding.stripe(100, 1, 4)]
+    with pytest.raises(ValueError):
+        sharding.interleaved_stripes(8, 0, 2, 0)
+
+
 def test_stripe_partition_properties():
     from ascendpathtracing_b200 import sharding
     for width in (1, 7, 8, 1024, 3840):

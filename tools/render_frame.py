@@ -24,7 +24,9 @@ ap.add_argument("--height", type=int, default=2160)
 ap.add_argument("--spp", type=int, default=1024)
 ap.add_argument("--depth", type=int, default=5)
 ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--materials", action="store_true")
+ap.add_argument("--materials", action="store_true", help="DIFF/SPEC/REFR + Russian roulette on smallpt's scene (C5, extension kernel)")
+ap.add_argument("--c4", action="store_true", help="BASELINE config C4: 10 k random spheres, all three materials, through the GPU-built BVH")
+ap.add_argument("--max-depth", type=int, default=64, help="bounce cap of the material kernels")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -35,9 +37,16 @@ if world > 1:
 W, H, S = a.width, a.height, a.spp // 4
 x0, x1 = sharding.stripe(W, rank, world)
 d_img = torch.zeros((H, x1 - x0, 3), dtype=torch.uint8, device="cuda")
-if a.materials:
+if a.c4:
+    nsph = 7 + 10000
+    d_sc = torch.from_numpy(pt.random_scene(10000, seed=12345)).cuda()
+    bvh = pt.Bvh(d_sc, nsph, nsph)  # every rank builds its own copy of the tree (4 ms)
+    p = pt.default_params(width=W, height=H, samples=S)
+    mp = pt.default_material_params(seed=1, max_depth=a.max_depth)
+    render = lambda: pt.render_image_mat_bvh(p, mp, bvh, d_img, x0=x0, x1=x1, cam_seed=2024, gamma=True)  # noqa: E731
+elif a.materials:
     p = pt.default_params(width=W, height=H, samples=S, sphere_count=9, sphere_stride=16)
-    mp = pt.default_material_params(seed=1)
+    mp = pt.default_material_params(seed=1, max_depth=a.max_depth)
     d_sc = torch.from_numpy(pt.smallpt_scene()).cuda()
     render = lambda: pt.render_image_mat(p, mp, d_sc, d_img, x0=x0, x1=x1, cam_seed=2024, gamma=True)  # noqa: E731
 else:
@@ -68,7 +77,8 @@ for _ in range(a.reps):
 if rank == 0:
     n = W * H * 4 * S
     best = min(times)
-    out = {"frame": f"{W}x{H}", "spp": 4 * S, "paths": n, "n_gpus": world, "mode": "materials" if a.materials else f"reference-parity depth {a.depth}",
+    out = {"frame": f"{W}x{H}", "spp": 4 * S, "paths": n, "n_gpus": world, "mode": (f"c4 10k spheres + BVH, depth cap {a.max_depth}" if a.c4 else f"materials depth cap {a.max_depth}" if a.materials
+                    else f"reference-parity depth {a.depth}"),
            "seconds": best, "mpaths_s": n / best / 1e6, "all_times": times, "image_mean": float(img.float().mean()),
            "image_sha_head": int(img.view(-1)[:4096].long().sum())}
     print(json.dumps(out), flush=True)
