@@ -240,9 +240,15 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t spp = 4LL * p->samples;
     const int64_t pix_begin = static_cast<int64_t>(x0) * p->height, pix_end = static_cast<int64_t>(x1) * p->height;
-    // Tile = whole pixels, up to 64 Mi paths (0.8 GB of workspace).  Large tiles keep the launch gaps and the persistent
-    // kernel's tail below a few percent.
-    const int64_t target_paths = 64LL << 20;
+    // Tile = whole pixels, up to 512 Mi paths (6.4 GB of workspace out of 180 GB).  Every launch of a persistent kernel
+    // ends in a tail in which all warps run out of fresh paths at about the same time and finish their last ones with
+    // ever fewer lanes busy: ~0.1 ms for the mirror kernel but 4-8 ms for the BVH material kernel (paths of up to 64
+    // bounces; profiles/r1_c4_tail.md), so a frame should be as few launches as memory allows.  PTB200_TILE_PATHS overrides.
+    static const int64_t target_paths = [] {
+        const char *e = getenv("PTB200_TILE_PATHS");
+        const long long v = e ? atoll(e) : 0;
+        return v > 0 ? static_cast<int64_t>(v) : (512LL << 20);
+    }();
     int64_t tile_pix = target_paths / spp;
     if (tile_pix < 1)
         tile_pix = 1;
