@@ -15,7 +15,7 @@ class PtParams(ctypes.Structure):
     """Run-time form of the reference's src/common.h constants (see include/ptb200.h)."""
     _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("samples", ctypes.c_int32), ("depth", ctypes.c_int32),
                 ("sphere_count", ctypes.c_int32), ("sphere_stride", ctypes.c_int32), ("light_index", ctypes.c_int32),
-                ("emission_scale", ctypes.c_float), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("emission_scale", ctypes.c_float), ("flags", ctypes.c_int32), ("column_step", ctypes.c_int32)]
 
     @property
     def n_paths(self):

@@ -235,6 +235,18 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
         return PTB200_OK;
     if ((spheres == nullptr && tree == nullptr) || image == nullptr)
         return fail(PTB200_EINVAL, "%s: NULL buffer", who);
+    // column_step k > 1: every k-th column from x0, into a dense [H][ceil((x1-x0)/k)][3] image.  The launch walks that dense
+    // frame; ray generation and the RNG keys map back to image columns / global path indices (pt_raygen.cuh).
+    const int32_t step = p->column_step > 1 ? p->column_step : 1;
+    if (p->column_step < 0)
+        return fail(PTB200_EINVAL, "%s: column_step must be >= 0", who);
+    if (step > 1 && uniforms != nullptr)
+        return fail(PTB200_EINVAL, "%s: a replayed random stream cannot be combined with column_step > 1", who);
+    const int32_t x_first = x0;
+    if (step > 1) {  // from here on [x0, x1) are columns of the dense frame
+        x1 = (x1 - x0 + step - 1) / step;
+        x0 = 0;
+    }
     if ((rc = check_device(who)) != PTB200_OK)
         return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -273,7 +285,14 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
         const int64_t npix = (pix_end - q < tile_pix) ? pix_end - q : tile_pix;
         const int64_t m = npix * spp;
         const double *u = uniforms ? uniforms + 2 * (q - pix_begin) * spp : nullptr;
-        const RayGenSource gen = make_raygen_source(*p, u, seed, q * spp, m);
+        RayGenSource gen = make_raygen_source(*p, u, seed, q * spp, m);
+        if (step > 1) {
+            if (!gen.fast_index) {  // tiles are whole pixels and below 2^31 paths, so only a frame of 2^31 pixels gets here
+                e = cudaErrorInvalidValue;
+                break;
+            }
+            gen.x_first = x_first, gen.x_step = step;
+        }
         // the tile is its own m-path problem for the trace kernel
         if (mp != nullptr)
             e = trace_materials(stream, *p, *mp, nullptr, reinterpret_cast<const float *>(spheres), cols, m, 0, m, static_cast<uint64_t>(q * spp), seg_stat,

@@ -52,6 +52,11 @@ struct RayGenSource {
     long long path0;
     int fast_index;        // path0 is a whole number of pixels and all indices fit 32 bits
     unsigned int pix_base; // path0 / (4*S) when fast_index
+    // Column stride (PtParams.column_step > 1): the launch walks a DENSE frame of every x_step-th column starting at x_first
+    // -- local column j is image column x_first + j * x_step -- and path0 / pix_base count in that dense frame.  The camera
+    // sees the image column, and every random number is keyed by the GLOBAL path index, so a strided render reproduces
+    // exactly those columns of the whole frame.  x_step == 1: x_first = 0 and local = global.
+    int x_first, x_step;
 };
 
 // gen_data.py:24-29; np.linalg.norm = sqrt of a left-to-right 3-term dot.  Host code: built with
@@ -98,6 +103,8 @@ inline RayGenSource make_raygen_source(const PtParams &p, const double *uniforms
     g.path0 = path0;
     g.fast_index = (path0 % spp == 0) && m < (1LL << 31) && (path0 + m) / spp < (1LL << 31);
     g.pix_base = g.fast_index ? static_cast<unsigned int>(path0 / spp) : 0u;
+    g.x_first = 0;
+    g.x_step = 1;
     return g;
 }
 
@@ -114,6 +121,18 @@ inline RayGenSource make_raygen_source_shifted(const RayGenSource &g, int64_t of
 }
 
 #ifdef __CUDACC__
+// Global path index ((((x*H + y)*2 + sy)*2 + sx)*S + k, gen_data.py:32-36) of element i of a strided launch (fast_index).
+__device__ __forceinline__ unsigned long long strided_global_path(const RayGenSource &g, unsigned int i) {
+    const RayGenArgs &a = g.a;
+    const unsigned int spp = 4u * static_cast<unsigned int>(a.s);
+    const unsigned int lp = a.by_spp.div(i);
+    const unsigned int pix = g.pix_base + lp;
+    const unsigned int xl = a.by_h.div(pix);
+    const unsigned int y = pix - xl * static_cast<unsigned int>(a.ih);
+    const unsigned long long x = static_cast<unsigned long long>(g.x_first) + static_cast<unsigned long long>(xl) * static_cast<unsigned int>(g.x_step);
+    return (x * static_cast<unsigned int>(a.ih) + y) * spp + (i - lp * spp);
+}
+
 // tent filter, gen_data.py:37-40: one square root per call (both branches take the root of a value in [0, 1])
 __device__ __forceinline__ double raygen_tent(double u) {
     const double r = __dmul_rn(2.0, u);
@@ -146,6 +165,7 @@ __device__ __forceinline__ void generate_ray(const RayGenSource &g, long long i,
         sy = static_cast<int>(sub >> 1);
         x = static_cast<int>(a.by_h.div(pix));
         y = static_cast<int>(pix - static_cast<unsigned int>(x) * static_cast<unsigned int>(a.ih));
+        x = g.x_first + x * g.x_step;  // dense column -> image column (identity unless strided)
     } else {
         long long r = (g.path0 + i) / a.s;
         sx = static_cast<int>(r & 1);
@@ -160,7 +180,8 @@ __device__ __forceinline__ void generate_ray(const RayGenSource &g, long long i,
         u1 = g.uniforms[2 * i];
         u2 = g.uniforms[2 * i + 1];
     } else {
-        philox_uniform2(g.seed, static_cast<uint64_t>(g.path0 + i), u1, u2);
+        const uint64_t gp = g.x_step > 1 ? strided_global_path(g, static_cast<unsigned int>(i)) : static_cast<uint64_t>(g.path0 + i);
+        philox_uniform2(g.seed, gp, u1, u2);
     }
     const double dx = raygen_tent(u1);
     const double dy = raygen_tent(u2);

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const float *__restrict__ 
 // r[4*half .. 4*half+3] in a float4 (block b of the run contributes a[8b + 4*half ..], in order), and the combine
 // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) is two in-lane adds and one shuffle.  Needs S % 8 == 0 (every block of NumPy's
 // recursion is then a whole number of 8-float groups, no sequential tails) and 16-byte aligned planes; anything else
-// takes the kernel above.  Same bits either way (tests compare both against the oracle).
+// takes the kernel above.  Same bits either way (the parity tests cover both).
 constexpr int kTileCols = 16, kTileRows = 16;
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }

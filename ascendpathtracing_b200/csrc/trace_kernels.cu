@@ -288,7 +288,9 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
         }
         if (active) {  // dead lanes of a finished range idle; live ones diverge by material inside
             segs++;
-            const bool ended = material_bounce<NS>(p, nsph, one, eps, rr_start, seed, path0 + mine, sh);
+            // RNG key: the global path index (a strided launch walks a dense frame of every k-th column, pt_raygen.cuh)
+            const unsigned long long pid = (GEN && c_gen.x_step > 1) ? strided_global_path(c_gen, mine) : path0 + mine;
+            const bool ended = material_bounce<NS>(p, nsph, one, eps, rr_start, seed, pid, sh);
             want = ended || p.depth >= max_depth;
         }
     }
@@ -456,7 +458,8 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
                 p.depth = pool.depth[s2];
                 mypath = pool.path[s2];
                 segs++;
-                ended = material_shade<true>(p, pool.tmin[s2], pool.idx[s2], rr_start, seed, path0 + mypath, nosh, bvh) || p.depth >= max_depth;
+                const unsigned long long pid = (GEN && c_gen.x_step > 1) ? strided_global_path(c_gen, mypath) : path0 + mypath;
+                ended = material_shade<true>(p, pool.tmin[s2], pool.idx[s2], rr_start, seed, pid, nosh, bvh) || p.depth >= max_depth;
                 if (ended) {
                     pl.col[0][mypath] = p.lr;
                     pl.col[1][mypath] = p.lg;

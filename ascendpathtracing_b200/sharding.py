@@ -53,6 +53,33 @@ def gather_interleaved(local, width, parts, group=None):
     return frame
 
 
+def strided_columns(width, rank, world):
+    """(x0, step, n_columns) of the finest interleave: rank r renders image columns r, r + world, r + 2 world, ... in ONE
+    launch (PtParams.column_step = world), so every rank sees the same mix of cheap and expensive columns and pays the
+    persistent kernel's tail once."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    return rank, world, len(range(rank, width, world))
+
+
+def gather_strided(local, width, group=None):
+    """All-gather of per-rank dense images [H, n_columns(rank), 3] rendered with strided_columns() into the [H, W, 3] frame."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    h = local.shape[0]
+    widest = -(-width // world)
+    pad = torch.zeros((h, widest, 3), dtype=local.dtype, device=local.device)
+    pad[:, :local.shape[1]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    frame = torch.empty((h, width, 3), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        n = len(range(r, width, world))
+        frame[:, r::world] = out[r][:, :n]
+    return frame
+
+
 def gather_stripes(local, width, group=None):
     """All-gather of per-rank stripes [H, x1-x0, 3] uint8 (torch tensors, any backend) into the full [H, W, 3] frame.
     Stripes may differ by one column, so each is padded to the widest before the collective."""

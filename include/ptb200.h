@@ -58,7 +58,9 @@ typedef struct PtParams {
     int32_t light_index;    /* sphere that ends a path (rt_helper.h:776), reference = 7 */
     float emission_scale;   /* final multiplier (render.cpp:194-196), reference = 12 */
     int32_t flags;          /* PTB200_F_* */
-    int32_t reserved;
+    int32_t column_step;    /* ptb200_render_image*: 0 or 1 = every column of [x0, x1); k > 1 = columns x0, x0+k, x0+2k, ... < x1
+                             * into a dense image of ceil((x1-x0)/k) columns (multi-GPU: rank r of G renders x0 = r, k = G in
+                             * ONE launch, evenly loaded whatever the scene).  Ignored by the other entry points. */
 } PtParams;
 
 enum {

@@ -97,6 +97,52 @@ def test_two_rank_interleaved_stripes_assemble(tmp_path, w, h, parts):
     assert np.array_equal(frame[0, :, 2], owner)
 
 
+def _worker_strided(rank, world, port, w, h, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from ascendpathtracing_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x0, step, ncols = sharding.strided_columns(w, rank, world)
+        local = np.zeros((h, ncols, 3), np.uint8)
+        for j in range(ncols):
+            local[:, j, 0] = (x0 + j * step) % 251
+            local[:, j, 1] = np.arange(h) % 251
+            local[:, j, 2] = rank
+        frame = sharding.gather_strided(torch.from_numpy(local), w)
+        if rank == 0:
+            np.save(os.path.join(outdir, "frame.npy"), frame.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("w,h", [(37, 4), (2, 3), (64, 2)])
+def test_two_rank_strided_columns_assemble(tmp_path, w, h):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker_strided, args=(2, port, w, h, str(tmp_path)), nprocs=2, join=True)
+    frame = np.load(tmp_path / "frame.npy")
+    assert np.array_equal(frame[:, :, 0], np.broadcast_to(np.arange(w) % 251, (h, w)))
+    assert np.array_equal(frame[:, :, 1], np.broadcast_to((np.arange(h) % 251)[:, None], (h, w)))
+    assert np.array_equal(frame[0, :, 2], np.arange(w) % 2)
+
+
+def test_strided_columns_cover_the_frame():
+    from ascendpathtracing_b200 import sharding
+    for width in (1, 5, 64, 1920):
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(width, int)
+            for r in range(world):
+                x0, step, n = sharding.strided_columns(width, r, world)
+                cols = x0 + step * np.arange(n)
+                assert (cols < width).all()
+                seen[cols] += 1
+            assert (seen == 1).all()
+
+
 def test_interleaved_partition_properties():
     from ascendpathtracing_b200 import sharding
     for width in (1, 7, 64, 1920, 3840):
