@@ -239,6 +239,63 @@ def test_resolve_bit_exact(pt, cuda, oracle, w, h, s):
         assert np.array_equal(d_part.cpu().numpy(), oracle.resolve(col, w, h, s)[:, x0:x1])
 
 
+@pytest.mark.parametrize("w,h,s", [(48, 32, 8), (64, 40, 16), (37, 50, 8), (32, 16, 256), (80, 17, 24)])
+def test_resolve_tiled_kernel_whole_and_ragged_tiles(pt, cuda, oracle, w, h, s):
+    """S % 8 == 0 takes the tiled resolve kernel (128-bit loads, 128-bit row stores): frames with whole 16 x 16 tiles, ragged
+    right / bottom edges, rows that are not 16-byte aligned (byte-store fallback) and stripes starting on / off a tile column."""
+    torch = cuda
+    rng = np.random.default_rng(w * 1000 + h * 10 + s)
+    p = pt.default_params(width=w, height=h, samples=s)
+    col = (rng.random(3 * p.n_paths) * 1.4 - 0.1).astype(np.float32)
+    want = oracle.resolve(col, w, h, s)
+    d_col = dev(torch, col)
+    d_img = torch.full((h, w, 3), 7, dtype=torch.uint8, device="cuda")
+    pt.resolve(p, d_col, d_img)
+    assert np.array_equal(d_img.cpu().numpy(), want)
+    for x0, x1 in [(16, w), (0, 32), (5, w - 3), (16, 32)]:
+        if not 0 <= x0 < x1 <= w:
+            continue
+        d_part = torch.full((h, x1 - x0, 3), 7, dtype=torch.uint8, device="cuda")
+        pt.resolve(p, d_col, d_part, x0=x0, x1=x1)
+        assert np.array_equal(d_part.cpu().numpy(), want[:, x0:x1]), (x0, x1)
+
+
+def test_small_tiles_split_the_frame_mid_column(pt, cuda, tmp_path):
+    """The production entry renders a frame in tiles of whole pixels; with the default 512 Mi-path tiles no test frame is ever
+    split, so a child process renders with PTB200_TILE_PATHS small enough to start tiles in the middle of image columns
+    (pixel ranges the tiled resolve kernel has to clip) and must produce the frame of the unsplit render, all three kernels."""
+    torch = cuda
+    import subprocess
+    import sys
+    w, h, s = 40, 36, 8
+    script = f"""
+import sys, numpy as np, torch
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import ascendpathtracing_b200 as pt
+w, h, s = {w}, {h}, {s}
+out = []
+img = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
+p = pt.default_params(width=w, height=h, samples=s)
+pt.render_image(p, torch.from_numpy(pt.default_scene()).cuda(), img, seed=3); out.append(img.cpu().numpy().copy())
+pm = pt.default_params(width=w, height=h, samples=s, sphere_count=9, sphere_stride=16)
+mp = pt.default_material_params(seed=2, max_depth=10)
+pt.render_image_mat(pm, mp, torch.from_numpy(pt.smallpt_scene()).cuda(), img, cam_seed=4); out.append(img.cpu().numpy().copy())
+bvh = pt.Bvh(torch.from_numpy(pt.random_scene(300)).cuda(), 307, 307)
+pt.render_image_mat_bvh(p, mp, bvh, img, cam_seed=4); out.append(img.cpu().numpy().copy())
+np.save(sys.argv[1], np.stack(out))
+"""
+    frames = {}
+    for name, tile in (("whole", ""), ("split", str(267 * 4 * s))):  # a tile = 267 pixels: not a multiple of h = 36
+        env = dict(os.environ)
+        if tile:
+            env["PTB200_TILE_PATHS"] = tile
+        out = tmp_path / f"{name}.npy"
+        subprocess.run([sys.executable, "-c", script, str(out)], check=True, env=env, timeout=600)
+        frames[name] = np.load(out)
+    assert np.array_equal(frames["whole"], frames["split"])
+    assert frames["whole"].std() > 1
+
+
 # ---- whole-job entries -------------------------------------------------------------------------------
 
 def test_render_host_entry(pt, cuda, oracle):
