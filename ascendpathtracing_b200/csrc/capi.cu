@@ -479,10 +479,12 @@ int ptb200_render_host(const PtParams *p, const float *rays_host, const float *s
     constexpr int kStreams = 4;
     static const int64_t chunk_paths = [] {  // PTB200_HOST_CHUNK overrides (experiments)
         const char *e = getenv("PTB200_HOST_CHUNK");
-        return e ? atoll(e) : (4LL << 20);
+        return e ? atoll(e) : (8LL << 20);
     }();
-    int64_t chunk = chunk_paths;  // paths per chunk: 96 MiB in, 48 MiB out (measured: 1 Mi-path chunks are no faster, 256 Ki-path
-                                  // chunks halve the rate; the call is bound by PCIe at ~45 GB/s host-to-device)
+    // Peak paths per chunk: 192 MiB in, 96 MiB out.  Measured on C2 (1.2 GB in, 0.6 GB out) with the ramped schedule below:
+    // 4 Mi 25.9 ms, 8 Mi 25.1, 16 Mi 25.0, 32 Mi 25.1; equal 4 Mi chunks without the ramps 26.7 ms.  The link itself moves
+    // the same bytes in 23.0 ms as two giant copies (52.5 GB/s in while 26.3 GB/s go out, tools/pcie_probe.py).
+    int64_t chunk = chunk_paths;
     if (chunk > n)
         chunk = n;
     const int nbuf = static_cast<int>((n + chunk - 1) / chunk < kStreams ? (n + chunk - 1) / chunk : kStreams);
@@ -511,9 +513,32 @@ int ptb200_render_host(const PtParams *p, const float *rays_host, const float *s
         for (int b = 1; b < nbuf && e == cudaSuccess; b++)
             e = cudaStreamWaitEvent(st[b], sph_ready, 0);
         PtParams cp = *p;
+        // Chunk schedule: the first chunk's upload and the last chunk's kernel + download overlap with nothing, so the
+        // schedule ramps up from chunk/8 and down again to chunk/8 (3 ms of exposed transfer with equal chunks on C2, 0.4 ms so).
+        std::vector<int64_t> sizes;
+        {
+            // peak chunk: the largest chunk / 2^j whose two ramps (chunk/8 ... peak/2 each) take at most half of the job
+            int64_t peak = chunk, first_c = chunk / 8 < 1024 ? chunk : chunk / 8;
+            while (peak > first_c && 2 * (peak - first_c) > n / 2)
+                peak /= 2;
+            int64_t left = n;
+            std::vector<int64_t> tail;
+            for (int64_t c = first_c; c < peak; c *= 2) {
+                sizes.push_back(c);
+                tail.push_back(c);
+                left -= 2 * c;
+            }
+            while (left > 0) {
+                const int64_t c = left < peak ? left : peak;
+                sizes.push_back(c);
+                left -= c;
+            }
+            sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
+        }
         int k = 0;
-        for (int64_t a = 0; a < n && e == cudaSuccess; a += chunk, k++) {
-            const int64_t m = (n - a < chunk) ? n - a : chunk;
+        int64_t a = 0;
+        for (size_t i = 0; i < sizes.size() && e == cudaSuccess; a += sizes[i], i++, k++) {
+            const int64_t m = sizes[i];
             const int b = k % nbuf;
             float *d_rays = d_buf[b], *d_cols = d_buf[b] + 6 * chunk;
             for (int c = 0; c < 6 && e == cudaSuccess; c++)
