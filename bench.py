@@ -200,7 +200,11 @@ def main():
     d_sph = torch.from_numpy(pt.default_scene()).cuda()
     d_col = torch.empty(3 * n, dtype=torch.float32, device="cuda")
     d_img = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
-    d_all = torch.zeros((world, H, W, 3), dtype=torch.uint8, device="cuda") if world > 1 else None
+    # N > 1: the stripes of step i are gathered while step i+1 is being traced (two image buffers; the gather runs on NCCL's
+    # stream).  Every gather completes inside the timed region: the loop waits for the last one before the closing event.
+    d_imgs = [d_img, torch.zeros_like(d_img)] if world > 1 else [d_img]
+    d_alls = [torch.zeros((world, H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+    gather = {"pending": None, "count": 0}
     torch.cuda.synchronize()
 
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -211,9 +215,18 @@ def main():
         pt.render_do_ex(p, d_rays, d_sph, d_col)   # launches: pack_scene + trace
         if i is not None:
             k_ev[i][1].record()
-        pt.resolve(p, d_col, d_img)                 # launch: resolve
+        slot = gather["count"] % len(d_imgs)
+        gather["count"] += 1
+        pt.resolve(p, d_col, d_imgs[slot])          # launch: resolve
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_img)  # final assembly of the 8-bit stripes over NVLink
+            if gather["pending"] is not None:
+                gather["pending"].wait()            # the previous step's gather (other buffer) ran beside this step's trace
+            gather["pending"] = dist.all_gather_into_tensor(d_alls[slot], d_imgs[slot], async_op=True)  # 8-bit stripes over NVLink
+
+    def drain():
+        if gather["pending"] is not None:
+            gather["pending"].wait()
+            gather["pending"] = None
 
     def fence():
         torch.cuda.synchronize()
@@ -223,6 +236,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    drain()
     fence()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -231,6 +245,7 @@ def main():
     t0.record()
     for i in range(args.steps):
         step(i)
+    drain()
     t1.record()
     fence()
     clocks = sampler.stop() if rank == 0 else None
@@ -318,7 +333,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "c2", "scene": "reference 8-sphere Cornell box", "width": W, "height": H, "spp": 4 * S, "depth": DEPTH,
                            "paths_per_gpu": n, "l2": "inputs larger than L2 (1.2 GB of rays per step vs 126 MB)",
-                           "step": "render_do_ex + resolve" + (" + NCCL all_gather of 8-bit stripes" if world > 1 else ""),
+                           "step": "render_do_ex + resolve" + (" + NCCL all_gather of 8-bit stripes (overlapped with the next step's trace)" if world > 1 else ""),
                            "rng": "counter-based (Philox4x32-10), rays resident in HBM"},
                 "grays_per_s": value * DEPTH / 1e3, "grays_note": "reference-equivalent segments (N*depth); early termination traces ~78% of them",
                 "roofline": roofline, "clocks": clocks, "gpu_launches": 3 * args.steps,
