@@ -715,10 +715,10 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
     if ((e = cudaGetLastError()) != cudaSuccess)
         return e;
     // Early termination and the fixed-depth loop give identical bits, so which one runs is a pure performance choice:
-    // lock-step lanes swap paths once per `depth` iterations (115 Gsegments/s), regenerating lanes every iteration
-    // (95-99 Gsegments/s) but they skip the settled part of every path: 22 % of the segments at depth 5, 13 % at depth 4.
-    // Measured on B200 (profiles/r1_depth_sweep.md): regeneration wins from depth 5 on (5.49 vs 5.77 ms at depth 5,
-    // 20.4 vs 107 ms at depth 50).
+    // lock-step lanes swap paths once per `depth` iterations (119-123 Gsegments/s), regenerating lanes every iteration
+    // (103-109 Gsegments/s) but they skip the settled part of every path: 21 % of the segments at depth 5, 13 % at depth 4.
+    // Measured on B200 (tools/early_crossover.py, 132.7 M paths): depth 3: 3.72 vs 3.50 ms (lock step wins), depth 4: 4.52 vs
+    // 4.54 (a tie), depth 5: 5.08 vs 5.58, depth 6: 5.56 vs 6.62, depth 50: 18.6 vs 100.8 -> regeneration from depth 5 on.
     static const int min_early_depth = [] {  // PTB200_EARLY_FROM_DEPTH overrides the crossover (experiments)
         const char *e = getenv("PTB200_EARLY_FROM_DEPTH");
         return e ? atoi(e) : 5;
