@@ -50,6 +50,58 @@ def test_bvh_first_hit_equals_brute_force(pt, cuda, oracle, n_random, eps):
     bvh.close()
 
 
+def test_bvh_axis_aligned_grazing_and_far_rays(pt, cuda, oracle):
+    """Rays the quantised slab test has to survive: direction components exactly 0 (1 / d = inf, NaN planes), rays aimed at a
+    sphere's silhouette (hit or miss decided by rounding noise: the padded boxes must never cull a brute-force hit), origins
+    on sphere centres, and origins far outside the tree (beyond 2^21 grid units: the exact fallback over all spheres)."""
+    torch = cuda
+    rng = np.random.default_rng(5)
+    n_random = 4000
+    scene = pt.random_scene(n_random)
+    nsph = 7 + n_random
+    sc = scene.reshape(11, -1)
+    bvh = pt.Bvh(dev(torch, scene), nsph, nsph)
+    m = 60000
+    o = np.stack([rng.uniform(1.5, 98.5, m), rng.uniform(0.5, 81.0, m), rng.uniform(0.5, 169.5, m)])
+    # 1. axis-aligned and plane-aligned directions
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [0.6, 0.8, 0], [0, -0.6, 0.8], [0.8, 0, -0.6]], dtype=np.float64).T
+    d1 = axes[:, rng.integers(0, axes.shape[1], m)]
+    # 2. grazing: aim at a random small sphere's silhouette (offset = radius, perpendicular to the line of sight)
+    k = rng.integers(7, nsph, m)
+    c = sc[1:4, k].astype(np.float64)
+    r = np.sqrt(sc[0, k].astype(np.float64))
+    los = c - o
+    los /= np.linalg.norm(los, axis=0)
+    perp = np.cross(los.T, rng.normal(size=(m, 3))).T
+    perp /= np.linalg.norm(perp, axis=0)
+    target = c + perp * r * rng.choice([0.999999, 1.0, 1.000001], m)
+    d2 = target - o
+    d2 /= np.linalg.norm(d2, axis=0)
+    # 3. origins exactly on sphere centres (inside a small sphere), random directions
+    o3 = sc[1:4, rng.integers(7, nsph, m)].astype(np.float64)
+    d3 = rng.normal(size=(3, m))
+    d3 /= np.linalg.norm(d3, axis=0)
+    # 4. far origins looking back at the scene, and a few absurd ones
+    far = rng.choice([3e3, 1e5, 1e7, 1e9], m)
+    d4 = rng.normal(size=(3, m))
+    d4 /= np.linalg.norm(d4, axis=0)
+    centre = np.array([[50.0], [40.0], [85.0]])
+    o4 = centre - d4 * far + rng.normal(size=(3, m)) * 20
+    rays = np.concatenate([np.concatenate([o, d1]), np.concatenate([o, d2]), np.concatenate([o3, d3]), np.concatenate([o4, d4])], axis=1).astype(np.float32)
+    n = rays.shape[1]
+    d_t = torch.zeros(n, dtype=torch.float32, device="cuda")
+    d_i = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    for eps in (1e-4, 0.1):
+        bvh.first_hit(dev(torch, rays.reshape(-1)), n, d_t, d_i, eps=eps)
+        torch.cuda.synchronize()
+        want_t, want_i = oracle.first_hit(rays, scene, nsph=nsph, eps=eps)
+        got_t, got_i = d_t.cpu().numpy(), d_i.cpu().numpy()
+        bad = np.flatnonzero((got_i != want_i) | (bits(got_t) != bits(want_t)))
+        assert bad.size == 0, (eps, bad[:10], got_i[bad[:10]], want_i[bad[:10]], got_t[bad[:10]], want_t[bad[:10]])
+    assert (want_i[m:2 * m] >= 7).mean() > 0.2   # the grazing rays do end on small spheres often enough to matter
+    bvh.close()
+
+
 def test_bvh_clustered_and_duplicate_spheres(pt, cuda, oracle):
     """Degenerate input for an LBVH: many coincident centres (identical Morton codes), touching and nested spheres."""
     torch = cuda
