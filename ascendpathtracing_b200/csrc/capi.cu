@@ -261,22 +261,30 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
         const long long v = e ? atoll(e) : 0;
         return v > 0 ? static_cast<int64_t>(v) : (512LL << 20);
     }();
-    int64_t tile_pix = target_paths / spp;
-    if (tile_pix < 1)
-        tile_pix = 1;
-    if (tile_pix > pix_end - pix_begin)
-        tile_pix = pix_end - pix_begin;
-    const int64_t tile_paths = tile_pix * spp;
     // Rays are generated inside the trace kernel (straight into its shared-memory ring) and never exist in HBM; only the
-    // per-path colours of a tile (12 B/path) are materialised between the trace and the resolve kernel.
+    // per-path colours of a tile (12 B/path) are materialised between the trace and the resolve kernel.  If the device
+    // cannot spare the workspace (other tenants, a smaller GPU) the tile is halved until it fits, down to 16 Mi paths.
     PtArena *arena = nullptr;
-    const size_t col_bytes = sizeof(float) * 3 * static_cast<size_t>(tile_paths);
-    if ((rc = workspace(col_bytes + 4096, &arena)) != PTB200_OK)
-        return rc;
-    float *rays = nullptr;
-    float *cols = static_cast<float *>(ptb200_arena_alloc(arena, col_bytes));
-    if (cols == nullptr)
-        return PTB200_ENOMEM;
+    float *rays = nullptr, *cols = nullptr;
+    int64_t tile_pix = 0;
+    for (int64_t want = target_paths;; want /= 2) {
+        tile_pix = want / spp;
+        if (tile_pix < 1)
+            tile_pix = 1;
+        if (tile_pix > pix_end - pix_begin)
+            tile_pix = pix_end - pix_begin;
+        const size_t col_bytes = sizeof(float) * 3 * static_cast<size_t>(tile_pix * spp);
+        rc = workspace(col_bytes + 4096, &arena);
+        if (rc == PTB200_OK) {
+            cols = static_cast<float *>(ptb200_arena_alloc(arena, col_bytes));
+            if (cols != nullptr)
+                break;
+            rc = PTB200_ENOMEM;
+        }
+        if (rc != PTB200_ENOMEM || want <= (16LL << 20) || tile_pix * spp <= (16LL << 20))
+            return rc;
+        cudaGetLastError();  // the failed cudaMalloc
+    }
     cudaError_t e = cudaSuccess;
     if (stats != nullptr)
         e = cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), stream);
