@@ -315,7 +315,10 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
 // other 32 slots split between the two queues, and shading runs exactly when tq is empty.
 // Queue traffic is batched: the walk loop runs until kRefillLanes lanes have finished before the warp stops to requeue.
 constexpr int kPool = 64;
-constexpr int kShortStack = 12;  // stack entries per lane in shared memory; deeper ones overflow to local memory
+#ifndef PTB_SHORT_STACK
+#define PTB_SHORT_STACK 12
+#endif
+constexpr int kShortStack = PTB_SHORT_STACK;  // stack entries per lane in shared memory; deeper ones overflow to local memory
 #ifndef PTB_REFILL_LANES
 #define PTB_REFILL_LANES 8
 #endif
@@ -777,6 +780,11 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
     const size_t smem = use_tree ? sizeof(WarpPool) * kWarpsPerBlock + sizeof(int) * kShortStack * kTraceThreads
                                  : sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
     const bool ten = !use_tree && (p.sphere_count == 9 || p.sphere_count == 10);  // smallpt's scene: unrolled pairs (index 9 is padding)
+    if (use_tree && smem > 48 * 1024) {  // only with non-default pool / stack sizes: opt in to more than 48 KB per block
+        if ((e = cudaFuncSetAttribute(trace_materials_bvh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess ||
+            (e = cudaFuncSetAttribute(trace_materials_bvh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+            return e;
+    }
     int occ = 0;
     // the fused-generation variants have the same resource footprint as the SoA ones (the generator is an out-of-line call)
     if ((e = use_tree ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_bvh_kernel<false>, kTraceThreads, smem)
