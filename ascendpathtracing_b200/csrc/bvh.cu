@@ -98,10 +98,10 @@ __global__ void hierarchy_kernel(const unsigned int *__restrict__ keys, const in
         nodes[0].parent = -1;
 }
 
-__device__ __forceinline__ Aabb sphere_box(const float4 g, float e_disc) {
+__device__ __forceinline__ Aabb sphere_box(const float4 g) {
     const float r2 = -g.w;
     const float r = sqrtf(fmaxf(r2, 0.0f));
-    const float pad = (sqrtf(r2 + e_disc) - r) + 1e-3f * r + 1e-3f;  // see pt_bvh.cuh
+    const float pad = 1e-3f * r + 1e-3f;  // slack for the slab arithmetic only; the exactness margin is per ray (pt_bvh.cuh)
     Aabb b;
     b.lo[0] = g.x - r - pad, b.lo[1] = g.y - r - pad, b.lo[2] = g.z - r - pad;
     b.hi[0] = g.x + r + pad, b.hi[1] = g.y + r + pad, b.hi[2] = g.z + r + pad;
@@ -119,7 +119,7 @@ __device__ __forceinline__ Aabb merge(const Aabb &a, const Aabb &b) {
 
 // One thread per leaf climbs towards the root; the second thread to reach a node (atomic counter) owns it, so both
 // children are complete by then.  own[] receives every internal node's box.
-__global__ void fit_kernel(const int *__restrict__ vals, const int *__restrict__ leaf_parent, int n, const float4 *__restrict__ geom, float e_disc,
+__global__ void fit_kernel(const int *__restrict__ vals, const int *__restrict__ leaf_parent, int n, const float4 *__restrict__ geom,
                            BvhNode *nodes, Aabb *own, unsigned int *visits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -130,8 +130,8 @@ __global__ void fit_kernel(const int *__restrict__ vals, const int *__restrict__
             return;  // first arrival: the sibling subtree is not done yet
         __threadfence();
         const int l = nodes[node].left, r = nodes[node].right;
-        const Aabb bl = l < 0 ? sphere_box(geom[~l], e_disc) : own[l];
-        const Aabb br = r < 0 ? sphere_box(geom[~r], e_disc) : own[r];
+        const Aabb bl = l < 0 ? sphere_box(geom[~l]) : own[l];
+        const Aabb br = r < 0 ? sphere_box(geom[~r]) : own[r];
         nodes[node].a = make_float4(bl.lo[0], bl.lo[1], bl.lo[2], bl.hi[0]);
         nodes[node].b = make_float4(bl.hi[1], bl.hi[2], br.lo[0], br.lo[1]);
         nodes[node].c = make_float4(br.lo[2], br.hi[0], br.hi[1], br.hi[2]);
@@ -204,7 +204,7 @@ using namespace ptb200;
 struct PtBvh {
     int device = 0;
     int n = 0, stride = 0, n_big = 0, n_small = 0;
-    float e_disc = 0.0f;
+    float centre[3] = {0, 0, 0}, radius = 0.0f, rmin = 0.0f, rmax = 0.0f;
     QNode *qnodes = nullptr;
     int *small_index = nullptr;
     float glo[3] = {0, 0, 0}, gscale[3] = {1, 1, 1};
@@ -217,7 +217,8 @@ struct PtBvh {
         s.qnodes = qnodes, s.geom = geom, s.color = color, s.emission = emission, s.big_index = big_index, s.small_index = small_index;
         s.n_big = n_big, s.n_small = n_small, s.root = 0, s.only_leaf = only_leaf;
         for (int c = 0; c < 3; c++)
-            s.glo[c] = glo[c], s.gscale[c] = gscale[c];
+            s.glo[c] = glo[c], s.gscale[c] = gscale[c], s.centre[c] = centre[c];
+        s.radius = radius, s.rmin = rmin, s.rmax = rmax;
         return s;
     }
 };
@@ -291,19 +292,27 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
     PtBvh *b = new PtBvh();
     cudaGetDevice(&b->device);
     b->n = count, b->stride = stride, b->n_big = static_cast<int>(big.size()), b->n_small = static_cast<int>(small.size());
-    double diag2 = 0.0;
     float ext[3] = {1.0f, 1.0f, 1.0f};
-    if (!small.empty())
+    if (!small.empty()) {
+        double rad2 = 0.0, rmin = INFINITY, rmax = 0.0;
         for (int c = 0; c < 3; c++) {
             const double dlt = static_cast<double>(hi[c]) - lo[c];
-            diag2 += dlt * dlt;
             ext[c] = static_cast<float>(dlt > 0 ? dlt : 1.0);
+            b->centre[c] = static_cast<float>(0.5 * (static_cast<double>(hi[c]) + lo[c]));
+            rad2 += 0.25 * dlt * dlt;
         }
-    b->e_disc = static_cast<float>(diag2 * (1.0 / 524288.0));  // 2^-19 D^2
-    // 16-bit grid of the traversal nodes: covers every padded box (pad <= sqrt(E) + 1e-3 * 100 + 1e-3) with room for the
-    // outward rounding and the kGridGrow units, so no plane ever clamps.
-    if (!small.empty()) {
-        const double margin = std::sqrt(static_cast<double>(b->e_disc)) + 1.2;
+        for (int i : small) {
+            const double r = std::sqrt(std::max(static_cast<double>(rows[i]), 0.0));
+            rmin = std::min(rmin, r);
+            rmax = std::max(rmax, r);
+        }
+        // bounding ball of all boxes (geometric boxes + the 1e-3 r + 1e-3 slack), a little generous; radii rounded the safe way
+        b->radius = static_cast<float>(std::sqrt(rad2) * 1.0001 + 0.5);
+        b->rmin = static_cast<float>(rmin * 0.9999);
+        b->rmax = static_cast<float>(rmax * 1.0001);
+        // 16-bit grid of the traversal nodes: covers every box (slack <= 1e-3 * 100 + 1e-3) with room for the outward rounding
+        // and the kGridGrow units, so no plane ever clamps.
+        const double margin = 1.2;
         for (int c = 0; c < 3; c++) {
             const double glo = static_cast<double>(lo[c]) - margin, ghi = static_cast<double>(hi[c]) + margin;
             b->glo[c] = static_cast<float>(glo);
@@ -367,7 +376,7 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) {
-            fit_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(d_vals, d_leaf_parent, ns, b->geom, b->e_disc, d_nodes, d_own, d_visits);
+            fit_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(d_vals, d_leaf_parent, ns, b->geom, d_nodes, d_own, d_visits);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) {

@@ -6,8 +6,14 @@
 // geometrically misses it by up to sqrt(r^2 + E) - r.  Hence
 //   * huge spheres (r^2 >= kBigR2: the 1e5-radius walls, the 600-radius light) never enter the tree: they stay in a
 //     brute-force list in the constant bank, tested pairwise with packed f32x2 like the 8-sphere scene;
-//   * every other sphere's box is its geometric box grown by pad = sqrt(r^2 + E) - r + 1e-3 r + 1e-3, E = 2^-19 * D^2 with
-//     D the diagonal of the scene's bounds (a 16x margin over the worst-case discriminant error at that distance);
+//   * a sphere's box is its geometric box plus a little slack (1e-3 r + 1e-3) for the slab arithmetic; the margin that
+//     exactness needs is applied PER RAY, because it depends on the ray: the reference's discriminant carries an absolute
+//     error proportional to |centre - origin|^2, plus |d|^2 - 1 times that when the direction is not exactly unit (mirror
+//     bounces are not renormalised), so a ray can "hit" a sphere its line misses by up to m = sqrt(r^2 + E) - r with
+//     E = (2^-19 + ||d|^2 - 1|) L^2, L = the farthest a sphere that can still beat the ray's current best hit can be.
+//     m is largest for the smallest sphere of the tree; the walk grows every box by that m, folded into the near / far
+//     constants of the slab FFMA (no instruction per step).  A fixed, scene-wide pad (the first version: 0.29 units in C4)
+//     swamps small spheres; the per-ray margin is 0.04 at 100 units and 0.004 at 30;
 //   * leaves run the exact scalar test, candidates are merged with the (t, index) order of the reference.
 //
 // What bounds traversal on B200 (ncu, profiles/r2_c4_*): incoherent rays make every node fetch touch one cache line per
@@ -17,8 +23,9 @@
 //   * decoding costs nothing: PRMT drops the 16 bits into the mantissa of 2^23 (0x4B000000 | q = 2^23 + q exactly), and
 //     the slab distance is ONE FFMA, t = (2^23 + q) * id + c with id = 1 / (d * scale) and c = -(2^23 + round(og)) * id
 //     (og = ray origin in grid units).  Rounding og to an integer and rounding c each move a plane by at most 0.504 grid
-//     units and the FMA's own rounding by less than 0.13 (origins within 2^21 units), together < kGridGrow = 2 minus the
-//     slack spent on the float evaluation of floor/ceil at build time: the test stays conservative.  A relative error of
+//     units, the FMA's own rounding by less than 0.13 (origins within 2^21 units) and folding the per-ray margin into c
+//     by another 0.5, together < kGridGrow = 3 minus the slack spent on the float evaluation of floor/ceil at build
+//     time: the test stays conservative.  A relative error of
 //     id scales both terms alike, so MUFU.RCP is good enough for it;
 //   * the near/far plane of each axis is picked by the PRMT selector (sign of d), not by min/max afterwards.
 // Origins further than 2^21 grid units from the tree (64 scene widths) fall back to an exact loop over all spheres.
@@ -32,7 +39,7 @@ namespace ptb200 {
 
 constexpr float kBigR2 = 1.0e4f;    // radius >= 100 stays out of the tree
 constexpr int kBvhStack = 64;       // Karras depth <= 30 key bits + 24 index bits (ptb200_bvh_build caps the count at 2^24)
-constexpr int kGridGrow = 2;        // grid units added on every side of a quantised box (see above)
+constexpr int kGridGrow = 3;        // grid units added on every side of a quantised box (see above)
 constexpr float kGridMax = 65535.0f;
 constexpr float kGridFar = 2097152.0f;  // 2^21: |og| beyond this -> exact fallback
 
@@ -60,28 +67,50 @@ struct BvhScene {
     const int *small_index;  // original indices of the spheres in the tree (ascending): the exact fallback's list
     int n_big, n_small, root, only_leaf;  // root: internal node 0 or, when n_small == 1, the leaf reference only_leaf
     float glo[3], gscale[3];              // grid = (world - glo) * gscale
+    float centre[3], radius;              // bounding ball of the tree's boxes (world units)
+    float rmin, rmax;                     // smallest / largest sphere radius in the tree
 };
 
-// Per-ray traversal constants (9 registers).
+// Per-ray traversal constants (12 registers).
 struct BvhRay {
     float idx, idy, idz;          // 1 / (d * gscale)
-    float cx, cy, cz;             // -(2^23 + round(og)) * id
+    float nx, ny, nz;             // near planes: -(2^23 + round(og)) * id - margin * |id|
+    float fx, fy, fz;             // far planes:  -(2^23 + round(og)) * id + margin * |id|
     unsigned int sx, sy, sz;      // PRMT selectors of the near plane per axis (far = near ^ 0x22)
-    bool far_origin;              // origin outside the range the 2^23 trick covers
+    bool far_origin;              // not coverable by the quantised walk (far / NaN origin, direction far from unit): exact loop
 };
 
-__device__ __forceinline__ BvhRay bvh_ray(const BvhScene &sc, float ox, float oy, float oz, float dx, float dy, float dz) {
+// tbest: the best hit so far (the brute-force list's, or 1e20): bounds how far a sphere that still matters can be.
+__device__ __forceinline__ BvhRay bvh_ray(const BvhScene &sc, float ox, float oy, float oz, float dx, float dy, float dz, float tbest) {
     BvhRay r;
     const float ogx = __fmul_rn(__fsub_rn(ox, sc.glo[0]), sc.gscale[0]);
     const float ogy = __fmul_rn(__fsub_rn(oy, sc.glo[1]), sc.gscale[1]);
     const float ogz = __fmul_rn(__fsub_rn(oz, sc.glo[2]), sc.gscale[2]);
-    r.far_origin = !(fmaxf(fmaxf(fabsf(ogx), fabsf(ogy)), fabsf(ogz)) <= kGridFar);  // NaN origins too
+    // Exactness margin (header).  The computed discriminant of a sphere at distance a = |centre - origin| differs from
+    // r^2 - (distance of the centre from the ray's line)^2 by at most 16 u a^2 + 2 u r^2 of rounding (u = 2^-24: three
+    // subtractions, two 3-term dot products, one square, two sums) plus | |d|^2 - 1 | a^2 of direction length; twice the
+    // rounding bound is used.  A sphere that can still replace the best hit t has a <= t |d| + r + m, and none is further
+    // than `reach`.
+    const float ex = ox - sc.centre[0], ey = oy - sc.centre[1], ez = oz - sc.centre[2];
+    const float reach = sqrtf(ex * ex + ey * ey + ez * ez) + sc.radius;
+    const float eta = fabsf((dx * dx + dy * dy + dz * dz) - 1.0f) + 4.0e-7f;  // | |d|^2 - 1 |, with room for its own rounding
+    const float k2 = 1.9073486e-6f + eta;                                       // 2^-19 + eta
+    const float by_hit = (tbest * (1.001f + 0.5f * eta) + sc.rmax + 0.01f) / (1.0f - sqrtf(k2)) * 1.001f;
+    const float L = fminf(by_hit, reach);
+    const float E = k2 * L * L + 2.3841858e-7f * sc.rmax * sc.rmax;             // ... + 2^-22 rmax^2
+    const float margin = 1.001f * (E / (sqrtf(sc.rmin * sc.rmin + E) + sc.rmin)) + 1e-6f;  // sqrt(rmin^2 + E) - rmin, rounded up
+    r.far_origin = !(fmaxf(fmaxf(fabsf(ogx), fabsf(ogy)), fabsf(ogz)) <= kGridFar) || !(eta <= 0.01f) || !(margin <= 64.0f);
     r.idx = mufu_rcp(__fmul_rn(dx, sc.gscale[0]));
     r.idy = mufu_rcp(__fmul_rn(dy, sc.gscale[1]));
     r.idz = mufu_rcp(__fmul_rn(dz, sc.gscale[2]));
-    r.cx = -__fmul_rn(__fadd_rn(ogx, 8388608.0f), r.idx);
-    r.cy = -__fmul_rn(__fadd_rn(ogy, 8388608.0f), r.idy);
-    r.cz = -__fmul_rn(__fadd_rn(ogz, 8388608.0f), r.idz);
+    const float cx = -__fmul_rn(__fadd_rn(ogx, 8388608.0f), r.idx);
+    const float cy = -__fmul_rn(__fadd_rn(ogy, 8388608.0f), r.idy);
+    const float cz = -__fmul_rn(__fadd_rn(ogz, 8388608.0f), r.idz);
+    const float mx = __fmul_rn(__fmul_rn(margin, sc.gscale[0]), fabsf(r.idx));  // margin in grid units times |id|
+    const float my = __fmul_rn(__fmul_rn(margin, sc.gscale[1]), fabsf(r.idy));
+    const float mz = __fmul_rn(__fmul_rn(margin, sc.gscale[2]), fabsf(r.idz));
+    r.nx = __fsub_rn(cx, mx), r.ny = __fsub_rn(cy, my), r.nz = __fsub_rn(cz, mz);
+    r.fx = __fadd_rn(cx, mx), r.fy = __fadd_rn(cy, my), r.fz = __fadd_rn(cz, mz);
     r.sx = dx < 0.0f ? 0x7632u : 0x7610u;
     r.sy = dy < 0.0f ? 0x7632u : 0x7610u;
     r.sz = dz < 0.0f ? 0x7632u : 0x7610u;
@@ -91,12 +120,12 @@ __device__ __forceinline__ BvhRay bvh_ray(const BvhScene &sc, float ox, float oy
 // Slab test of one quantised child box.  NaN planes (0 * inf, inf - inf on an axis the ray does not move along) drop out
 // of the 3-input min/max, which only makes the test more permissive.
 __device__ __forceinline__ bool hit_qbox(const BvhRay &r, unsigned int wx, unsigned int wy, unsigned int wz, float tbest, float &tnear) {
-    const float nx = __fmaf_rn(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx)), r.idx, r.cx);
-    const float ny = __fmaf_rn(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy)), r.idy, r.cy);
-    const float nz = __fmaf_rn(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz)), r.idz, r.cz);
-    const float fx = __fmaf_rn(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx ^ 0x22u)), r.idx, r.cx);
-    const float fy = __fmaf_rn(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy ^ 0x22u)), r.idy, r.cy);
-    const float fz = __fmaf_rn(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz ^ 0x22u)), r.idz, r.cz);
+    const float nx = __fmaf_rn(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx)), r.idx, r.nx);
+    const float ny = __fmaf_rn(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy)), r.idy, r.ny);
+    const float nz = __fmaf_rn(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz)), r.idz, r.nz);
+    const float fx = __fmaf_rn(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx ^ 0x22u)), r.idx, r.fx);
+    const float fy = __fmaf_rn(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy ^ 0x22u)), r.idy, r.fy);
+    const float fz = __fmaf_rn(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz ^ 0x22u)), r.idz, r.fz);
     const float tn = fmaxf(fmaxf(nx, ny), nz);
     const float tf = fminf(fminf(fx, fy), fz);
     tnear = tn;
@@ -182,6 +211,31 @@ static __device__ __noinline__ void bvh_all_leaves(const BvhScene &sc, float ox,
         bvh_leaf(sc, __ldg(sc.small_index + k), ox, oy, oz, dx, dy, dz, eps, tmin, idx);
 }
 
+// The same, by a whole warp for ONE ray (all 32 lanes must call it with that ray's values): lanes test interleaved spheres
+// with coalesced loads and the best (t, index) is reduced in the reference's order.  A leaked path that bounces off the
+// outside of a 1e5-radius wall ends up 10^5 units away, where the binary32 test reports hits all over the scene, so nothing
+// can be culled for it; alone, one lane took 0.15 s for such a ray in a 10^6-sphere scene (dependent loads), the warp 1 ms.
+__device__ __forceinline__ void bvh_all_leaves_warp(const BvhScene &sc, unsigned int lane, float ox, float oy, float oz, float dx, float dy,
+                                                    float dz, float eps, float &tmin, int &idx) {
+    const float t_in = tmin;
+    const int i_in = idx;
+    for (int k = static_cast<int>(lane); k < sc.n_small; k += 32)
+        bvh_leaf(sc, __ldg(sc.small_index + k), ox, oy, oz, dx, dy, dz, eps, tmin, idx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float t2 = __shfl_xor_sync(0xffffffffu, tmin, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (t2 < tmin || (t2 == tmin && i2 < idx)) {
+            tmin = t2;
+            idx = i2;
+        }
+    }
+    if (!(tmin < t_in) && !(tmin == t_in && tmin < kMiss && idx < i_in)) {  // nothing beat what the ray came in with
+        tmin = t_in;
+        idx = i_in;
+    }
+}
+
 struct LocalStack {  // per-lane stack in local memory
     int *v;
     int sp;
@@ -216,7 +270,7 @@ __device__ __forceinline__ void bvh_nearest(const BvhScene &sc, float ox, float 
         bvh_leaf(sc, ~sc.only_leaf, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
         return;
     }
-    const BvhRay r = bvh_ray(sc, ox, oy, oz, dx, dy, dz);
+    const BvhRay r = bvh_ray(sc, ox, oy, oz, dx, dy, dz, tmin);
     if (r.far_origin) {
         bvh_all_leaves(sc, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
         return;

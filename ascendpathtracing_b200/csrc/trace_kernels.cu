@@ -539,10 +539,12 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
         if (tq_count > 0 && busy != 0xffffffffu) {
             const unsigned int imask = ~busy;
             const int rank = __popc(imask & lt);
+            float ox = 0.0f, oy = 0.0f, oz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 1.0f;
+            bool exact_loop = false;  // a ray the quantised walk does not cover (pt_bvh.cuh): every sphere, by the whole warp
             if (!cur && rank < tq_count) {
                 slot = pool.tq[tq_count - 1 - rank];
-                const float ox = pool.ray[0][slot], oy = pool.ray[1][slot], oz = pool.ray[2][slot];
-                const float dx = pool.ray[3][slot], dy = pool.ray[4][slot], dz = pool.ray[5][slot];
+                ox = pool.ray[0][slot], oy = pool.ray[1][slot], oz = pool.ray[2][slot];
+                dx = pool.ray[3][slot], dy = pool.ray[4][slot], dz = pool.ray[5][slot];
                 tmin = pool.tmin[slot];
                 idx = pool.idx[slot];
                 cur = true;
@@ -551,11 +553,22 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
                 if (bvh.n_small == 1) {
                     bvh_leaf(bvh, ~bvh.only_leaf, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
                 } else if (bvh.n_small > 1) {
-                    r = bvh_ray(bvh, ox, oy, oz, dx, dy, dz);
-                    if (r.far_origin)
-                        bvh_all_leaves(bvh, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
-                    else
+                    r = bvh_ray(bvh, ox, oy, oz, dx, dy, dz, tmin);
+                    exact_loop = r.far_origin;
+                    if (!exact_loop)
                         node = 0;
+                }
+            }
+            for (unsigned int todo = __ballot_sync(0xffffffffu, exact_loop); todo != 0u; todo &= todo - 1u) {
+                const int leader = __ffs(todo) - 1;
+                float t = __shfl_sync(0xffffffffu, tmin, leader);
+                int i = __shfl_sync(0xffffffffu, idx, leader);
+                bvh_all_leaves_warp(bvh, lane, __shfl_sync(0xffffffffu, ox, leader), __shfl_sync(0xffffffffu, oy, leader),
+                                    __shfl_sync(0xffffffffu, oz, leader), __shfl_sync(0xffffffffu, dx, leader),
+                                    __shfl_sync(0xffffffffu, dy, leader), __shfl_sync(0xffffffffu, dz, leader), eps, t, i);
+                if (static_cast<int>(lane) == leader) {
+                    tmin = t;
+                    idx = i;
                 }
             }
             const int taken = __popc(imask);
