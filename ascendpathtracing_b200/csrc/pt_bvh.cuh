@@ -28,7 +28,8 @@
 //     time: the test stays conservative.  A relative error of
 //     id scales both terms alike, so MUFU.RCP is good enough for it;
 //   * the near/far plane of each axis is picked by the PRMT selector (sign of d), not by min/max afterwards.
-// Origins further than 2^21 grid units from the tree (64 scene widths) fall back to an exact loop over all spheres.
+// Origins further than 2^21 grid units from the tree (64 scene widths), directions more than 1 % off unit length and NaNs
+// take an exact loop over all spheres (run by the whole warp for one ray in the wavefront kernel).
 //
 // Layout: LBVH (Morton order, Karras 2012); a reference < 0 is a leaf (~ref = sphere).  Traversal: near child first,
 // leaf tests and stack policy supplied by the caller.

@@ -166,9 +166,11 @@ PTB200_API int ptb200_render_image_mat(const PtParams *p, const PtMaterialParams
 
 typedef struct PtBvh PtBvh;
 /* Builds an LBVH (Morton order, Karras hierarchy) over the spheres of an 11-row SoA [11][stride] on the device.
- * Spheres of radius >= 100 (the 1e5-radius walls, the light) stay in a brute-force list; the tree's boxes are padded so
- * that the nearest hit equals the brute-force loop's bit for bit (t, index, lowest index on ties) for rays that start
- * inside the scene.  Synchronous; the handle owns its device memory and keeps no reference to `spheres`. */
+ * Spheres of radius >= 100 (the 1e5-radius walls, the light) stay in a brute-force list.  The nearest hit through the tree
+ * equals the brute-force loop's bit for bit (t, index, lowest index on ties): every ray widens the boxes by the margin the
+ * reference's binary32 test needs at its distance and direction length, and rays no margin can cover (origins 64 scene
+ * widths away, directions more than 1 % off unit length, NaNs) are tested against every sphere.
+ * Synchronous; the handle owns its device memory and keeps no reference to `spheres`. */
 PTB200_API int ptb200_bvh_build(const uint8_t *spheres, int32_t count, int32_t stride, void *stream, PtBvh **out);
 PTB200_API int ptb200_bvh_destroy(PtBvh *bvh);
 PTB200_API int ptb200_bvh_info(const PtBvh *bvh, int32_t *n_spheres, int32_t *n_big, int32_t *n_small, int32_t *n_nodes);
