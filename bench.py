@@ -279,7 +279,7 @@ def main():
             e_ms = float(t[0])
         assert torch.equal(h_col.view(torch.int32), d_col.cpu().view(torch.int32)), "e2e result differs from the device-resident result"
         e2e = {"value": n * world / (e_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": 24 * n + 512, "d2h_bytes_per_step": 12 * n,
-               "ms_per_step": e_ms, "steps": e_steps, "api": "ptb200_render_host (pinned host rays in, host colours out, 3-stream chunked overlap)"}
+               "ms_per_step": e_ms, "steps": e_steps, "api": "ptb200_render_host (pinned host rays in, host colours out, 4 streams, chunks ramped up and down so that upload, kernel and download overlap)"}
         del h_rays, h_col
         # The whole run.sh-equivalent pipeline through one C-ABI call: scene (512 B, host) in, 8-bit stripe (host) out;
         # rays are generated on the device (counter-based RNG), traced and resolved tile by tile, nothing else crosses PCIe.
