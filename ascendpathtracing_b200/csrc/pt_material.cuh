@@ -125,6 +125,12 @@ __device__ __forceinline__ bool material_shade(MatPath &p, float tmin, int idx, 
     p.tg = __fmul_rn(p.tg, fg);
     p.tb = __fmul_rn(p.tb, fb);
     const int mat = static_cast<int>(ctr.w);
+    // Two of the three materials end in "normalise a vector": the diffuse direction, the refracted direction.  The branches
+    // only BUILD that vector (w); one normalisation after them serves both (a warp almost always holds both kinds of lane, and
+    // run inside the branches the ~45 instructions were issued twice, the second time for two or three lanes).
+    float wx = 0.0f, wy = 0.0f, wz = 1.0f;
+    float rx = 0.0f, ry = 0.0f, rz = 0.0f, ddn = 0.0f;
+    bool refract = false, into = false;
     if (mat == kMatDiff) {
         float sn, cs;
         sincos2pi(u1, sn, cs);
@@ -140,47 +146,49 @@ __device__ __forceinline__ bool material_shade(MatPath &p, float tmin, int idx, 
         const float vy = __fsub_rn(__fmul_rn(nlz, ux), __fmul_rn(nlx, uz));
         const float vz = __fsub_rn(__fmul_rn(nlx, uy), __fmul_rn(nly, ux));
         const float a = __fmul_rn(cs, r2s), bq = __fmul_rn(sn, r2s), cq = __fsqrt_rn(__fsub_rn(1.0f, u2));
-        float ndx = __fadd_rn(__fadd_rn(__fmul_rn(ux, a), __fmul_rn(vx, bq)), __fmul_rn(nlx, cq));
-        float ndy = __fadd_rn(__fadd_rn(__fmul_rn(uy, a), __fmul_rn(vy, bq)), __fmul_rn(nly, cq));
-        float ndz = __fadd_rn(__fadd_rn(__fmul_rn(uz, a), __fmul_rn(vz, bq)), __fmul_rn(nlz, cq));
-        normalize_rn(ndx, ndy, ndz);
-        p.dx = ndx, p.dy = ndy, p.dz = ndz;
+        wx = __fadd_rn(__fadd_rn(__fmul_rn(ux, a), __fmul_rn(vx, bq)), __fmul_rn(nlx, cq));
+        wy = __fadd_rn(__fadd_rn(__fmul_rn(uy, a), __fmul_rn(vy, bq)), __fmul_rn(nly, cq));
+        wz = __fadd_rn(__fadd_rn(__fmul_rn(uz, a), __fmul_rn(vz, bq)), __fmul_rn(nlz, cq));
     } else {
         const float k2 = __fadd_rn(dn, dn);
-        const float rx = __fsub_rn(p.dx, __fmul_rn(nx, k2)), ry = __fsub_rn(p.dy, __fmul_rn(ny, k2)), rz = __fsub_rn(p.dz, __fmul_rn(nz, k2));
-        if (mat == kMatSpec) {
-            p.dx = rx, p.dy = ry, p.dz = rz;
-        } else {  // REFR
-            const bool into = dot_rn(nx, ny, nz, nlx, nly, nlz) > 0.0f;
+        rx = __fsub_rn(p.dx, __fmul_rn(nx, k2)), ry = __fsub_rn(p.dy, __fmul_rn(ny, k2)), rz = __fsub_rn(p.dz, __fmul_rn(nz, k2));
+        if (mat != kMatSpec) {  // REFR
+            into = dot_rn(nx, ny, nz, nlx, nly, nlz) > 0.0f;
             const float nnt = into ? (1.0f / 1.5f) : 1.5f;
-            const float ddn = dot_rn(p.dx, p.dy, p.dz, nlx, nly, nlz);
+            ddn = dot_rn(p.dx, p.dy, p.dz, nlx, nly, nlz);
             const float cos2t = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(nnt, nnt), __fsub_rn(1.0f, __fmul_rn(ddn, ddn))));
-            if (cos2t < 0.0f) {  // total internal reflection
-                p.dx = rx, p.dy = ry, p.dz = rz;
-            } else {
+            if (!(cos2t < 0.0f)) {  // else total internal reflection: the mirror direction below
                 const float sgn = into ? 1.0f : -1.0f;
                 const float kk = __fmul_rn(sgn, __fadd_rn(__fmul_rn(ddn, nnt), __fsqrt_rn(cos2t)));
-                float tx = __fsub_rn(__fmul_rn(p.dx, nnt), __fmul_rn(nx, kk));
-                float ty = __fsub_rn(__fmul_rn(p.dy, nnt), __fmul_rn(ny, kk));
-                float tz = __fsub_rn(__fmul_rn(p.dz, nnt), __fmul_rn(nz, kk));
-                normalize_rn(tx, ty, tz);
-                const float r0 = 0.04f;
-                const float c = __fsub_rn(1.0f, into ? -ddn : dot_rn(tx, ty, tz, nx, ny, nz));
-                const float c2 = __fmul_rn(c, c);
-                const float c5 = __fmul_rn(__fmul_rn(c2, c2), c);
-                const float re = __fadd_rn(r0, __fmul_rn(1.0f - 0.04f, c5));
-                const float trn = __fsub_rn(1.0f, re);
-                const float pr = __fadd_rn(0.25f, __fmul_rn(0.5f, re));
-                if (u4 < pr) {
-                    const float rp = __fdiv_rn(re, pr);
-                    p.tr = __fmul_rn(p.tr, rp), p.tg = __fmul_rn(p.tg, rp), p.tb = __fmul_rn(p.tb, rp);
-                    p.dx = rx, p.dy = ry, p.dz = rz;
-                } else {
-                    const float tp = __fdiv_rn(trn, __fsub_rn(1.0f, pr));
-                    p.tr = __fmul_rn(p.tr, tp), p.tg = __fmul_rn(p.tg, tp), p.tb = __fmul_rn(p.tb, tp);
-                    p.dx = tx, p.dy = ty, p.dz = tz;
-                }
+                wx = __fsub_rn(__fmul_rn(p.dx, nnt), __fmul_rn(nx, kk));
+                wy = __fsub_rn(__fmul_rn(p.dy, nnt), __fmul_rn(ny, kk));
+                wz = __fsub_rn(__fmul_rn(p.dz, nnt), __fmul_rn(nz, kk));
+                refract = true;
             }
+        }
+    }
+    if (mat == kMatDiff || refract)
+        normalize_rn(wx, wy, wz);
+    if (mat == kMatDiff) {
+        p.dx = wx, p.dy = wy, p.dz = wz;
+    } else if (!refract) {  // SPEC, or REFR under total internal reflection
+        p.dx = rx, p.dy = ry, p.dz = rz;
+    } else {
+        const float r0 = 0.04f;
+        const float c = __fsub_rn(1.0f, into ? -ddn : dot_rn(wx, wy, wz, nx, ny, nz));
+        const float c2 = __fmul_rn(c, c);
+        const float c5 = __fmul_rn(__fmul_rn(c2, c2), c);
+        const float re = __fadd_rn(r0, __fmul_rn(1.0f - 0.04f, c5));
+        const float trn = __fsub_rn(1.0f, re);
+        const float pr = __fadd_rn(0.25f, __fmul_rn(0.5f, re));
+        if (u4 < pr) {
+            const float rp = __fdiv_rn(re, pr);
+            p.tr = __fmul_rn(p.tr, rp), p.tg = __fmul_rn(p.tg, rp), p.tb = __fmul_rn(p.tb, rp);
+            p.dx = rx, p.dy = ry, p.dz = rz;
+        } else {
+            const float tp = __fdiv_rn(trn, __fsub_rn(1.0f, pr));
+            p.tr = __fmul_rn(p.tr, tp), p.tg = __fmul_rn(p.tg, tp), p.tb = __fmul_rn(p.tb, tp);
+            p.dx = wx, p.dy = wy, p.dz = wz;
         }
     }
     p.ox = xx, p.oy = xy, p.oz = xz;
