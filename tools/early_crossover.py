@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Lock step vs regeneration of the reference-parity kernel at depth 2..6 (run with PTB200_EARLY_FROM_DEPTH=1 so that both
+modes can be selected at every depth): where the library's crossover (depth 5) comes from."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 import ascendpathtracing_b200 as pt

@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Two renders of a random-sphere scene of the given size through the BVH at 480x270, 16 spp: the command ncu is pointed at for
+profiles of the traversal kernel at 10^5 / 10^6 spheres (profiles/r1_bvh_1m_ncu_summary.txt).  usage: profile_bvh_big.py N_SPHERES"""
 import sys, torch, numpy as np
 sys.path.insert(0,'/root/repo')
 import ascendpathtracing_b200 as pt
