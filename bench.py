@@ -15,7 +15,8 @@ Printed JSON (one line, rank 0): value = paths of all ranks / max-over-ranks dev
 roofline of the trace kernel (algorithmic FLOPs = N*(depth*(19*8+33)+3)) against the FFMA peak
 measured live on this GPU by the library's dependent-free micro-kernel; e2e = the same metric through
 ptb200_render_host with pinned HOST buffers (H2D of rays and D2H of colours inside the timed region);
-cpu_baseline = the reference's own kernel (oracle/_ref, compiled from the reference sources) on the host cores.
+cpu_baseline = the reference's own kernel (oracle/_ref, compiled from the reference sources) on the host cores, timed on a
+bounded sample of C2 (the same frame at 16 spp instead of 64).
 """
 import argparse
 import json
@@ -34,8 +35,10 @@ sys.path.insert(0, ROOT)
 W, H, S, DEPTH, NSPH = 1024, 768, 16, 5, 8
 FLOPS_PER_PATH = DEPTH * (19 * NSPH + 33) + 3  # 928, SURVEY.md 8a/8d
 BYTES_PER_PATH = 36
-CPU_SAMPLE = (1024, 1024, 1, 5)                # 4 194 304 paths of the same scene/camera/depth (~0.8 s on 8 host threads)
-CPU_SAMPLE_SMALL = (256, 256, 1, 5)            # 262 144 paths: used by --impl reference when --steps is large
+# Bounded samples of C2 for the CPU legs (the reference's sizes are compile-time constants: one prebuilt oracle/_ref artefact each)
+CPU_SAMPLE = (1024, 768, 4, 5)                 # the C2 frame at 16 spp = 12 582 912 paths: ~2.3 s on 8 host threads, ~18 s of CPU work
+CPU_SAMPLE_MEDIUM = (1024, 1024, 1, 5)         # 4 194 304 paths of the same scene/camera/depth (~0.8 s on 8 host threads)
+CPU_SAMPLE_SMALL = (256, 256, 1, 5)            # 262 144 paths: used by --impl reference when --steps is very large
 
 
 def peaks():
@@ -129,7 +132,8 @@ def run_reference_arm(args, rank, emit):
     cores = host_threads()
     threads = min(8, cores)  # the reference runs 8 blocks (src/main.cpp:18): at most 8-way parallel
     # bounded sample per step, sized so that the whole run ends within a few minutes whatever --steps is
-    sample = CPU_SAMPLE if (args.steps + args.warmup) <= 120 else CPU_SAMPLE_SMALL
+    total = args.steps + args.warmup
+    sample = CPU_SAMPLE if total <= 40 else CPU_SAMPLE_MEDIUM if total <= 250 else CPU_SAMPLE_SMALL
     for _ in range(args.warmup):
         cpu_reference_run(threads, sample)
     tot_t, tot_n, kind = 0.0, 0, "reference"
@@ -207,7 +211,7 @@ def main():
     gather = {"pending": None, "count": 0}
     torch.cuda.synchronize()
 
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k_ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]  # before trace, after trace, after resolve
 
     def step(i=None):
         if i is not None:
@@ -218,6 +222,8 @@ def main():
         slot = gather["count"] % len(d_imgs)
         gather["count"] += 1
         pt.resolve(p, d_col, d_imgs[slot])          # launch: resolve
+        if i is not None:
+            k_ev[i][2].record()
         if world > 1:
             if gather["pending"] is not None:
                 gather["pending"].wait()            # the previous step's gather (other buffer) ran beside this step's trace
@@ -250,7 +256,8 @@ def main():
     fence()
     clocks = sampler.stop() if rank == 0 else None
     ms = t0.elapsed_time(t1)
-    trace_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    trace_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in k_ev]))
+    resolve_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in k_ev]))
     if world > 1:
         t = torch.tensor([ms, trace_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -328,7 +335,13 @@ def main():
                     "exact_mode_ceiling": "every op is a singly rounded FADD/FMUL (no FFMA): at most 0.5 of the FFMA-FLOP peak",
                     "fadd_fmul_issue_peak_gops": fadd_gops, "ffma_issue_peak_gops": ffma_gops,
                     "hbm": {"achieved_gbs": BYTES_PER_PATH * n / (trace_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                            "frac": (BYTES_PER_PATH * n / (trace_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None}}
+                            "frac": (BYTES_PER_PATH * n / (trace_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None},
+                    # the framebuffer kernel (colours -> 8-bit image) is the HBM-bound one: 12 B/path read once, 3 B/pixel written
+                    "resolve": {"bound": "hbm", "kernel": "resolve_tiles_kernel (128-bit loads, 128-bit coalesced row stores)",
+                                "kernel_ms": resolve_ms, "bytes": 12 * n + 3 * W * H,
+                                "achieved": (12 * n + 3 * W * H) / (resolve_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": ((12 * n + 3 * W * H) / (resolve_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)"}}
         line = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "c2", "scene": "reference 8-sphere Cornell box", "width": W, "height": H, "spp": 4 * S, "depth": DEPTH,

@@ -41,7 +41,8 @@ DEFAULT_CONFIGS = [
     (64, 64, 4, 5),     # SAMPLES > 1 (resolve order)
     (64, 64, 1, 10),    # depth sweep
     (64, 64, 1, 50),
-    (1024, 1024, 1, 5), # 4 194 304 paths: bounded sample of C2 for the CPU baseline
+    (1024, 1024, 1, 5), # 4 194 304 paths: bounded sample of C2 for the reference arm at many steps
+    (1024, 768, 4, 5),  # 12 582 912 paths: the C2 frame at 16 spp, the CPU baseline's sample (~18 s of CPU work)
 ]
 
 
