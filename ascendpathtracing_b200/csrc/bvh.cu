@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "pt_bvh.cuh"
@@ -18,17 +19,18 @@ struct Aabb {
 
 namespace {
 
-__device__ __forceinline__ unsigned int expand_bits(unsigned int v) {  // 10 bits -> every third bit
-    v = (v * 0x00010001u) & 0xFF0000FFu;
-    v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u;
-    v = (v * 0x00000005u) & 0x49249249u;
-    return v;
-}
+// Which axis each of the 30 key bits halves, most significant first.  A fixed x/y/z interleave gives cells with the aspect
+// ratio of the scene's bounds; here every bit halves the axis along which the cells are currently longest (host: morton_plan),
+// so the cells - and with them the boxes of the upper tree levels - stay as close to cubes as the bounds allow.
+constexpr int kKeyBits = 30;
+struct MortonPlan {
+    unsigned char axis[kKeyBits];
+    int nbits[3];  // bits each axis receives in total
+};
 
 // AoS copies of the per-sphere data (original index order) + Morton keys of the small spheres.
 __global__ void prepare_kernel(const float *__restrict__ sph, int n, int stride, float4 *geom, float4 *color, float4 *emission, const int *small_index,
-                               int n_small, float3 lo, float3 inv_extent, unsigned int *keys, int *vals) {
+                               int n_small, float3 lo, float3 inv_extent, MortonPlan plan, unsigned int *keys, int *vals) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         geom[i] = make_float4(sph[1 * stride + i], sph[2 * stride + i], sph[3 * stride + i], -sph[0 * stride + i]);
@@ -39,10 +41,20 @@ __global__ void prepare_kernel(const float *__restrict__ sph, int n, int stride,
         const int k = small_index[i];
         const float x = (sph[1 * stride + k] - lo.x) * inv_extent.x, y = (sph[2 * stride + k] - lo.y) * inv_extent.y,
                     z = (sph[3 * stride + k] - lo.z) * inv_extent.z;
-        const unsigned int xi = static_cast<unsigned int>(fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f));
-        const unsigned int yi = static_cast<unsigned int>(fminf(fmaxf(y * 1024.0f, 0.0f), 1023.0f));
-        const unsigned int zi = static_cast<unsigned int>(fminf(fmaxf(z * 1024.0f, 0.0f), 1023.0f));
-        keys[i] = (expand_bits(xi) << 2) | (expand_bits(yi) << 1) | expand_bits(zi);
+        const float f[3] = {x, y, z};
+        unsigned int q[3];
+        int left[3];
+        for (int c = 0; c < 3; c++) {
+            const float cells = static_cast<float>(1u << plan.nbits[c]);
+            q[c] = static_cast<unsigned int>(fminf(fmaxf(f[c] * cells, 0.0f), cells - 1.0f));
+            left[c] = plan.nbits[c];
+        }
+        unsigned int key = 0;
+        for (int bit = 0; bit < kKeyBits; bit++) {
+            const int c = plan.axis[bit];
+            key = (key << 1) | ((q[c] >> --left[c]) & 1u);
+        }
+        keys[i] = key;
         vals[i] = k;
     }
 }
@@ -320,6 +332,30 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
         }
     }
 
+    // Morton key layout: every bit halves the currently longest cell edge (ties: x, y, z).  PTB200_MORTON_INTERLEAVE=1 forces
+    // the classic fixed interleave (experiments).
+    MortonPlan plan;
+    {
+        static const bool fixed = [] {
+            const char *v = getenv("PTB200_MORTON_INTERLEAVE");
+            return v != nullptr && atoi(v) != 0;
+        }();
+        double cell[3] = {ext[0], ext[1], ext[2]};
+        plan.nbits[0] = plan.nbits[1] = plan.nbits[2] = 0;
+        for (int bit = 0; bit < kKeyBits; bit++) {
+            int c = bit % 3;
+            if (!fixed) {
+                c = 0;
+                for (int a = 1; a < 3; a++)
+                    if (cell[a] > cell[c])
+                        c = a;
+            }
+            plan.axis[bit] = static_cast<unsigned char>(c);
+            plan.nbits[c]++;
+            cell[c] *= 0.5;
+        }
+    }
+
     auto dmalloc = [&](void **p, size_t bytes) { return e == cudaSuccess ? (e = cudaMalloc(p, bytes ? bytes : 16)) : e; };
     BvhNode *d_nodes = nullptr;
     int *d_vals_in = nullptr, *d_vals = nullptr, *d_leaf_parent = nullptr;
@@ -356,7 +392,7 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
     if (e == cudaSuccess) {
         const int threads = 256, blocks = (std::max(count, ns) + threads - 1) / threads;
         prepare_kernel<<<blocks, threads, 0, stream>>>(sph, count, stride, b->geom, b->color, b->emission, d_small, ns, make_float3(lo[0], lo[1], lo[2]),
-                                                       make_float3(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]), d_keys_in, d_vals_in);
+                                                       make_float3(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]), plan, d_keys_in, d_vals_in);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess && ns == 1) {
