@@ -134,6 +134,8 @@ def run_reference_arm(args, rank, emit):
     # bounded sample per step, sized so that the whole run ends within a few minutes whatever --steps is
     total = args.steps + args.warmup
     sample = CPU_SAMPLE if total <= 40 else CPU_SAMPLE_MEDIUM if total <= 250 else CPU_SAMPLE_SMALL
+    if os.environ.get("PTB200_BENCH_CPU_SAMPLE") == "small":  # tests/test_bench_contract.py: the contract, not the number
+        sample = CPU_SAMPLE_SMALL
     for _ in range(args.warmup):
         cpu_reference_run(threads, sample)
     tot_t, tot_n, kind = 0.0, 0, "reference"
