@@ -708,7 +708,7 @@ int ptb200_write_ppm(const char *path, int32_t width, int32_t height, const uint
 }
 
 int ptb200_measure_fp32(int32_t kind, int32_t iters, double *gops_out, double *ms_out) {
-    if (gops_out == nullptr || ms_out == nullptr || iters < 1 || kind < 0 || kind > 13)
+    if (gops_out == nullptr || ms_out == nullptr || iters < 1 || kind < 0 || kind > 17)
         return fail(PTB200_EINVAL, "ptb200_measure_fp32: bad argument");
     int rc = check_device("ptb200_measure_fp32");
     if (rc != PTB200_OK)

@@ -13,11 +13,14 @@ constexpr int kUnroll = 8;
 template <int KIND> __global__ void __launch_bounds__(256) peak_kernel(int iters, float x, float y, float *out) {
     float a[kChains];
     float2 a2[kChains];
+    unsigned int b[kChains];
 #pragma unroll
     for (int j = 0; j < kChains; j++) {
         a[j] = 1.0f + 0.001f * (threadIdx.x + j);
         a2[j] = make_float2(a[j], a[j] + 0.5f);
+        b[j] = threadIdx.x * 2654435761u + j;
     }
+    const unsigned int m1 = __float_as_uint(x), m2 = __float_as_uint(y);
     const float2 x2 = make_float2(x, x), y2 = make_float2(y, y);
     for (int it = 0; it < iters; it++) {
 #pragma unroll
@@ -61,6 +64,17 @@ template <int KIND> __global__ void __launch_bounds__(256) peak_kernel(int iters
                 } else if (KIND == 13) {  // FMNMX (ALU pipe) alone
                     a[j] = fminf(a[j], x) ;
                     a[j] = fmaxf(a[j], y) ;
+                } else if (KIND == 14) {  // FFMA2 + one LOP3: does a packed op hold the issue port for one cycle or for two?
+                    a2[j] = __ffma2_rn(a2[j], x2, y2);
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[j]) : "r"(m1), "r"(m2));
+                } else if (KIND == 15) {  // FFMA2 with three distinct 64-bit register sources (operand bandwidth / bank conflicts)
+                    a2[j] = __ffma2_rn(a2[j], a2[(j + 1) % kChains], a2[(j + 3) % kChains]);
+                } else if (KIND == 16) {  // FFMA2 + scalar FADD + LOP3: 3 FP32-pipe cycles, 3 (or 4) issue cycles
+                    a2[j] = __ffma2_rn(a2[j], x2, y2);
+                    a[j] = __fadd_rn(a[j], y);
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[j]) : "r"(m1), "r"(m2));
+                } else if (KIND == 17) {  // FMUL2 and FADD2 on distinct registers: the trace kernel's two-source packed ops
+                    a2[j] = __fmul2_rn(a2[j], a2[(j + 1) % kChains]);
                 }
             }
         }
@@ -68,7 +82,7 @@ template <int KIND> __global__ void __launch_bounds__(256) peak_kernel(int iters
     float s = 0.0f;
 #pragma unroll
     for (int j = 0; j < kChains; j++)
-        s += a[j] + a2[j].x + a2[j].y;
+        s += a[j] + a2[j].x + a2[j].y + static_cast<float>(b[j]);
     if (s == 123.456f)
         out[0] = s;  // never true in practice; keeps the chains alive
 }
@@ -107,6 +121,10 @@ cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms_out) {
         case 11: return run<11>(it, grid, nullptr);
         case 12: return run<12>(it, grid, nullptr);
         case 13: return run<13>(it, grid, nullptr);
+        case 14: return run<14>(it, grid, nullptr);
+        case 15: return run<15>(it, grid, nullptr);
+        case 16: return run<16>(it, grid, nullptr);
+        case 17: return run<17>(it, grid, nullptr);
         default: return cudaErrorInvalidValue;
         }
     };
@@ -132,6 +150,8 @@ cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms_out) {
     if (kind == 10) per_step = 4.0;               // FMUL2 (2) + 2 FADD
     if (kind == 11) per_step = 2.0;               // counts the FADD2 lanes only; the 4 ALU ops ride along
     if (kind == 13) per_step = 2.0;
+    if (kind == 14 || kind == 15 || kind == 17) per_step = 2.0;  // the packed instruction's lanes; the LOP3 rides along
+    if (kind == 16) per_step = 3.0;                               // FFMA2 (2) + FADD (1)
     const double ops = static_cast<double>(grid) * 256.0 * iters * kUnroll * kChains * per_step;
     *gops = ops / (ms * 1e-3) / 1e9;
     *ms_out = ms;

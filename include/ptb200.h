@@ -225,7 +225,8 @@ PTB200_API int ptb200_write_ppm(const char *path, int32_t width, int32_t height,
 /* Measures FP32 issue throughput on the current device with dependent-free register-only kernels.
  * kind: 0 FFMA, 1 FADD/FMUL alternating, 2 FFMA2 (packed f32x2), 3 FADD2/FMUL2 alternating,
  *       4 FADD + FSETP/FSEL mix, 5 rsqrtf, 6 IEEE sqrt (__fsqrt_rn), 7 IEEE div (__fdiv_rn), 8 FMUL2, 9 FADD2,
- *       10 FMUL2 + 2 scalar FADD (the exact kernel's pattern), 11 FADD2 + 2x(FSETP+FSEL), 12 MUFU.RSQ, 13 FMNMX.
+ *       10 FMUL2 + 2 scalar FADD (the exact kernel's pattern), 11 FADD2 + 2x(FSETP+FSEL), 12 MUFU.RSQ, 13 FMNMX,
+ *       14 FFMA2 + LOP3, 15 FFMA2 with three register sources, 16 FFMA2 + FADD + LOP3, 17 FMUL2 with two register sources.
  * Writes giga-operations per second (one packed op counts as 2 lane-ops; FFMA counts as 1 op here --
  * multiply by 2 for FLOP) and the kernel milliseconds. */
 PTB200_API int ptb200_measure_fp32(int32_t kind, int32_t iters, double *gops_out, double *ms_out);

@@ -8,7 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ascendpathtracing_b200 as pt  # noqa: E402
 
 KINDS = ["FFMA", "FMUL+FADD alternating", "FFMA2 (packed f32x2)", "FMUL2+FADD2 alternating", "FADD + FSETP/FSEL", "MUFU.RSQ", "sqrt.rn (IEEE)",
-         "div.rn (IEEE)", "FMUL2 alone", "FADD2 alone", "FMUL2 + 2 scalar FADD", "FADD2 + 2x(FSETP+FSEL) [FADD2 lanes counted]", "MUFU.RSQ (pure)", "FMNMX x2 (ALU pipe)"]
+         "div.rn (IEEE)", "FMUL2 alone", "FADD2 alone", "FMUL2 + 2 scalar FADD", "FADD2 + 2x(FSETP+FSEL) [FADD2 lanes counted]", "MUFU.RSQ (pure)", "FMNMX x2 (ALU pipe)",
+         "FFMA2 + LOP3 [FFMA2 lanes counted]", "FFMA2, three distinct register sources", "FFMA2 + FADD + LOP3 [FP32 lanes counted]",
+         "FMUL2, two distinct register sources"]
 out = {}
 for k, name in enumerate(KINDS):
     best = 0.0
