@@ -222,7 +222,8 @@ struct PtBvh {
     float glo[3] = {0, 0, 0}, gscale[3] = {1, 1, 1};
     float4 *geom = nullptr, *color = nullptr, *emission = nullptr;
     int *big_index = nullptr;
-    float *big_soa = nullptr;  // [11][16] SoA of the big spheres for the constant-bank pack
+    float *big_soa = nullptr;  // [11][1024] SoA of the big spheres for the constant-bank pack
+    void *block = nullptr;     // the ONE device allocation all of the arrays above are carved from
     int only_leaf = 0;
     BvhScene scene() const {
         BvhScene s;
@@ -247,13 +248,7 @@ extern "C" {
 int ptb200_bvh_destroy(PtBvh *b) {
     if (b == nullptr)
         return PTB200_OK;
-    cudaFree(b->qnodes);
-    cudaFree(b->small_index);
-    cudaFree(b->geom);
-    cudaFree(b->color);
-    cudaFree(b->emission);
-    cudaFree(b->big_index);
-    cudaFree(b->big_soa);
+    cudaFree(b->block);
     delete b;
     return PTB200_OK;
 }
@@ -356,29 +351,70 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
         }
     }
 
-    auto dmalloc = [&](void **p, size_t bytes) { return e == cudaSuccess ? (e = cudaMalloc(p, bytes ? bytes : 16)) : e; };
-    BvhNode *d_nodes = nullptr;
-    int *d_vals_in = nullptr, *d_vals = nullptr, *d_leaf_parent = nullptr;
-    unsigned int *d_keys_in = nullptr, *d_keys = nullptr, *d_visits = nullptr;
-    Aabb *d_own = nullptr;
-    void *d_tmp = nullptr;
+    // Device memory: ONE allocation for everything the handle keeps and one block for the build's temporaries, the latter
+    // from the library's workspace arena when it can serve it (no driver call at all), else one cudaMalloc.  A build used to
+    // make 16 cudaMalloc and 9 cudaFree calls, which on a busy driver cost more than the kernels (2-8 ms for 10^4 spheres,
+    // 10-180 ms for 10^5).
     const int ns = b->n_small, nb = b->n_big;
-    dmalloc(reinterpret_cast<void **>(&b->geom), sizeof(float4) * count);
-    dmalloc(reinterpret_cast<void **>(&b->color), sizeof(float4) * count);
-    dmalloc(reinterpret_cast<void **>(&b->emission), sizeof(float4) * count);
-    dmalloc(reinterpret_cast<void **>(&b->big_index), sizeof(int) * std::max(nb, 1));
-    dmalloc(reinterpret_cast<void **>(&b->big_soa), sizeof(float) * 11 * 1024);
-    dmalloc(reinterpret_cast<void **>(&d_nodes), sizeof(BvhNode) * std::max(ns - 1, 1));
-    dmalloc(reinterpret_cast<void **>(&b->qnodes), sizeof(QNode) * std::max(ns - 1, 1));
-    dmalloc(reinterpret_cast<void **>(&b->small_index), sizeof(int) * std::max(ns, 1));
+    size_t keep_bytes = 0, temp_bytes = 0;
+    auto carve = [](size_t &total, size_t bytes) {  // 256-byte aligned offsets
+        const size_t off = total;
+        total += (bytes + 255) & ~static_cast<size_t>(255);
+        return off;
+    };
+    const size_t ns1 = static_cast<size_t>(std::max(ns, 1)), nn1 = static_cast<size_t>(std::max(ns - 1, 1));
+    const size_t o_geom = carve(keep_bytes, sizeof(float4) * count), o_color = carve(keep_bytes, sizeof(float4) * count),
+                 o_emis = carve(keep_bytes, sizeof(float4) * count), o_big = carve(keep_bytes, sizeof(int) * std::max(nb, 1)),
+                 o_soa = carve(keep_bytes, sizeof(float) * 11 * 1024), o_qn = carve(keep_bytes, sizeof(QNode) * nn1),
+                 o_small = carve(keep_bytes, sizeof(int) * ns1);
+    size_t cub_bytes = 0;
+    if (ns >= 2)  // size query only: no pointer is touched
+        e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<const unsigned int *>(nullptr), static_cast<unsigned int *>(nullptr),
+                                            static_cast<const int *>(nullptr), static_cast<int *>(nullptr), ns, 0, kKeyBits, stream);
+    const size_t o_nodes = carve(temp_bytes, sizeof(BvhNode) * nn1), o_keys_in = carve(temp_bytes, sizeof(unsigned int) * ns1),
+                 o_keys = carve(temp_bytes, sizeof(unsigned int) * ns1), o_vals_in = carve(temp_bytes, sizeof(int) * ns1),
+                 o_vals = carve(temp_bytes, sizeof(int) * ns1), o_parent = carve(temp_bytes, sizeof(int) * ns1),
+                 o_visits = carve(temp_bytes, sizeof(unsigned int) * ns1), o_own = carve(temp_bytes, sizeof(Aabb) * ns1),
+                 o_cub = carve(temp_bytes, cub_bytes ? cub_bytes : 16);
+    char *keep = nullptr, *temp = nullptr;
+    PtArena *arena = nullptr;
+    bool temp_from_arena = false;
+    if (e == cudaSuccess)
+        e = cudaMalloc(reinterpret_cast<void **>(&keep), keep_bytes);
+    if (e == cudaSuccess) {
+        if (workspace(temp_bytes + 256, &arena) == PTB200_OK && (temp = static_cast<char *>(ptb200_arena_alloc(arena, temp_bytes))) != nullptr)
+            temp_from_arena = true;
+        else
+            e = cudaMalloc(reinterpret_cast<void **>(&temp), temp_bytes);
+    }
+    auto release_temp = [&] {
+        if (temp == nullptr)
+            return;
+        if (temp_from_arena)
+            ptb200_arena_free(arena, temp);
+        else
+            cudaFree(temp);
+        temp = nullptr;
+    };
+    if (e != cudaSuccess) {
+        cudaFree(keep);
+        release_temp();
+        delete b;
+        return e == cudaErrorMemoryAllocation ? fail(PTB200_ENOMEM, "ptb200_bvh_build: out of device memory") : fail_cuda(e, "ptb200_bvh_build");
+    }
+    b->block = keep;
+    b->geom = reinterpret_cast<float4 *>(keep + o_geom), b->color = reinterpret_cast<float4 *>(keep + o_color);
+    b->emission = reinterpret_cast<float4 *>(keep + o_emis), b->big_index = reinterpret_cast<int *>(keep + o_big);
+    b->big_soa = reinterpret_cast<float *>(keep + o_soa), b->qnodes = reinterpret_cast<QNode *>(keep + o_qn);
+    b->small_index = reinterpret_cast<int *>(keep + o_small);
+    BvhNode *const d_nodes = reinterpret_cast<BvhNode *>(temp + o_nodes);
+    unsigned int *const d_keys_in = reinterpret_cast<unsigned int *>(temp + o_keys_in), *const d_keys = reinterpret_cast<unsigned int *>(temp + o_keys);
+    int *const d_vals_in = reinterpret_cast<int *>(temp + o_vals_in), *const d_vals = reinterpret_cast<int *>(temp + o_vals);
+    int *const d_leaf_parent = reinterpret_cast<int *>(temp + o_parent);
+    unsigned int *const d_visits = reinterpret_cast<unsigned int *>(temp + o_visits);
+    Aabb *const d_own = reinterpret_cast<Aabb *>(temp + o_own);
+    void *const d_tmp = temp + o_cub;
     int *const d_small = b->small_index;
-    dmalloc(reinterpret_cast<void **>(&d_keys_in), sizeof(unsigned int) * std::max(ns, 1));
-    dmalloc(reinterpret_cast<void **>(&d_keys), sizeof(unsigned int) * std::max(ns, 1));
-    dmalloc(reinterpret_cast<void **>(&d_vals_in), sizeof(int) * std::max(ns, 1));
-    dmalloc(reinterpret_cast<void **>(&d_vals), sizeof(int) * std::max(ns, 1));
-    dmalloc(reinterpret_cast<void **>(&d_leaf_parent), sizeof(int) * std::max(ns, 1));
-    dmalloc(reinterpret_cast<void **>(&d_visits), sizeof(unsigned int) * std::max(ns, 1));
-    dmalloc(reinterpret_cast<void **>(&d_own), sizeof(Aabb) * std::max(ns, 1));
     if (e == cudaSuccess && nb > 0)
         e = cudaMemcpyAsync(b->big_index, big.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess && ns > 0)
@@ -399,12 +435,8 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
         b->only_leaf = ~small[0];
     }
     if (e == cudaSuccess && ns >= 2) {
-        size_t tmp_bytes = 0;
-        e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys_in, d_keys, d_vals_in, d_vals, ns, 0, 30, stream);
-        if (e == cudaSuccess)
-            e = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
-        if (e == cudaSuccess)
-            e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys_in, d_keys, d_vals_in, d_vals, ns, 0, 30, stream);
+        size_t tmp_bytes = cub_bytes;
+        e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys_in, d_keys, d_vals_in, d_vals, ns, 0, kKeyBits, stream);
         if (e == cudaSuccess)
             e = cudaMemsetAsync(d_visits, 0, sizeof(unsigned int) * ns, stream);
         if (e == cudaSuccess) {
@@ -423,10 +455,12 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
             e = cudaGetLastError();
         }
     }
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(stream);
-    cudaFree(d_nodes), cudaFree(d_keys_in), cudaFree(d_keys), cudaFree(d_vals_in), cudaFree(d_vals), cudaFree(d_leaf_parent), cudaFree(d_visits),
-        cudaFree(d_own), cudaFree(d_tmp);
+    {  // always: the temporaries go back to the arena only once nothing can touch them any more
+        const cudaError_t es = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess)
+            e = es;
+    }
+    release_temp();
     if (e != cudaSuccess) {
         ptb200_bvh_destroy(b);
         return e == cudaErrorMemoryAllocation ? fail(PTB200_ENOMEM, "ptb200_bvh_build: out of device memory") : fail_cuda(e, "ptb200_bvh_build");

@@ -66,13 +66,17 @@ int check_device(const char *who) {
     return PTB200_OK;
 }
 
+}  // namespace
+
 // ---- per-device workspace arena (grown on demand) ----------------------------------------------------
+namespace {
 struct Workspace {
     PtArena *arena = nullptr;
     size_t capacity = 0;
 };
 Workspace g_ws[64];
 std::mutex g_ws_mu;
+}  // namespace
 
 // Returns an arena with at least `bytes` free in one block; recreates (after a device sync) when too small.
 int workspace(size_t bytes, PtArena **out) {
@@ -100,7 +104,6 @@ int workspace(size_t bytes, PtArena **out) {
     return PTB200_OK;
 }
 
-}  // namespace
 }  // namespace ptb200
 
 using namespace ptb200;

@@ -46,6 +46,10 @@ cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *
 // fp32_peak.cu
 cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms);
 
+// capi.cu -- the per-device workspace arena (csrc/arena.cu), grown on demand: an arena with at least `bytes` free in one
+// block.  Fails with PTB200_ENOMEM when it would have to grow while blocks are still in use.
+int workspace(size_t bytes, PtArena **out);
+
 // error plumbing (capi.cu)
 int fail(int code, const char *fmt, ...);
 int fail_cuda(cudaError_t e, const char *what);
