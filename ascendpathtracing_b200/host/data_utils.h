@@ -5,6 +5,7 @@
 // wrappers over the C ABI (ptb200_read_file / ptb200_write_file), which carries the reference's semantics.
 #ifndef PTB200_DATA_UTILS_H
 #define PTB200_DATA_UTILS_H
+#include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <iomanip>
@@ -22,9 +23,20 @@ typedef enum {
     INT64_T = 9, UINT64_T = 10, DOUBLE = 11, BOOL = 12, STRING = 13, COMPLEX64 = 16, COMPLEX128 = 17, BF16 = 27
 } printDataType;
 
-#define INFO_LOG(fmt, args...) fprintf(stdout, "[INFO]  " fmt "\n", ##args)
-#define WARN_LOG(fmt, args...) fprintf(stdout, "[WARN]  " fmt "\n", ##args)
-#define ERROR_LOG(fmt, args...) fprintf(stdout, "[ERROR]  " fmt "\n", ##args)
+// Same names, same output as the reference's log macros (one line on stdout: tag, two blanks, message).
+namespace ptb200_detail {
+__attribute__((format(printf, 2, 3))) inline void LogLine(const char *tag, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    fputs(tag, stdout);
+    vfprintf(stdout, fmt, ap);
+    fputc('\n', stdout);
+    va_end(ap);
+}
+}  // namespace ptb200_detail
+#define INFO_LOG(...) ptb200_detail::LogLine("[INFO]  ", __VA_ARGS__)
+#define WARN_LOG(...) ptb200_detail::LogLine("[WARN]  ", __VA_ARGS__)
+#define ERROR_LOG(...) ptb200_detail::LogLine("[ERROR]  ", __VA_ARGS__)
 
 #define CHECK_CUDA(x)                                                                                               \
     do {                                                                                                            \
