@@ -36,3 +36,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_other_ranks_exit_quietly():
     out = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, args=("--gpus", "2"))
     assert out.strip() == ""
+
+
+def test_tools_and_bench_compile():
+    """The measurement scripts are run by hand on the GPU box: at least keep them syntactically alive."""
+    import glob
+    import py_compile
+    for path in sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]:
+        py_compile.compile(path, doraise=True)
