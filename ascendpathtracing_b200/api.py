@@ -91,6 +91,9 @@ def lib():
         "render_do_mat_bvh": (c.c_int, [PP, c.POINTER(PtMaterialParams), vp, vp, vp, vp, i64, i64, u64, vp]),
         "ptb200_render_image_mat_bvh": (c.c_int, [PP, c.POINTER(PtMaterialParams), vp, vp, u64, i32, i32, i32, vp, vp]),
         "ptb200_random_scene": (c.c_int, [i32, u32, i32, vp]),
+        "ptb200_render_host_multi": (c.c_int, [PP, vp, i32, vp, vp, vp, vp]),
+        "ptb200_render_image_multi": (c.c_int, [PP, vp, i32, i32, vp, i32, vp, u64, vp, vp, vp]),
+        "ptb200_scene_layout": (c.c_int, [vp, sz, c.POINTER(i32), c.POINTER(i32), c.POINTER(i32)]),
         "ptb200_arena_create": (c.c_int, [sz, c.POINTER(vp)]),
         "ptb200_arena_wrap": (c.c_int, [vp, sz, c.POINTER(vp)]),
         "ptb200_arena_destroy": (c.c_int, [vp]),
@@ -208,6 +211,43 @@ def render_image(p, spheres, image_out, x0=0, x1=None, uniforms=None, seed=0, st
 def render_host(p, rays_host, spheres_host, colors_host):
     """Host buffers (numpy arrays or pinned torch CPU tensors) in and out; synchronous."""
     _check(lib().ptb200_render_host(ctypes.byref(p), _ptr(rays_host), _ptr(spheres_host), _ptr(colors_host)))
+
+
+# ---- one process, several GPUs ---------------------------------------------------------------------------
+
+def _device_list(devices):
+    if devices is None:
+        raise ValueError("devices: an int (0..n-1) or a list of device indices")
+    if isinstance(devices, int):
+        return None, devices
+    arr = (ctypes.c_int32 * len(devices))(*devices)
+    return arr, len(devices)
+
+
+def render_host_multi(p, devices, rays_host, spheres_host, colors_host):
+    """ptb200_render_host over several GPUs of this process (contiguous path slices). Returns [wall_ms, ms of device 0, ...]."""
+    arr, n = _device_list(devices)
+    ms = (ctypes.c_double * (1 + n))()
+    _check(lib().ptb200_render_host_multi(ctypes.byref(p), arr, n, _ptr(rays_host), _ptr(spheres_host), _ptr(colors_host), ms))
+    return list(ms)
+
+
+def render_image_multi(p, devices, spheres_host, image_out, seed=0, mp=None, use_bvh=False, gamma=False):
+    """The whole frame on several GPUs of this process (strided columns, P2P gather on devices[0]).  image_out: numpy array /
+    pinned CPU tensor / CUDA tensor on devices[0], [H][W][3] uint8.  Returns (stats [paths, segments], [wall_ms, device ms...])."""
+    arr, n = _device_list(devices)
+    ms = (ctypes.c_double * (1 + n))()
+    st = (ctypes.c_uint64 * 2)()
+    _check(lib().ptb200_render_image_multi(ctypes.byref(p), ctypes.byref(mp) if mp is not None else None, 1 if use_bvh else 0, 1 if gamma else 0,
+                                           arr, n, _ptr(spheres_host), seed, _ptr(image_out), st, ms))
+    return [int(st[0]), int(st[1])], list(ms)
+
+
+def scene_layout(nbytes, scene=None):
+    """(count, stride, rows) of a spheres.bin of nbytes bytes (512 = the reference's file; else 44-byte columns)."""
+    c, s, r = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _check(lib().ptb200_scene_layout(_ptr(scene), nbytes, ctypes.byref(c), ctypes.byref(s), ctypes.byref(r)))
+    return c.value, s.value, r.value
 
 
 # ---- material extension ----------------------------------------------------------------------------------

@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptb200.so")
-SOURCES = ["capi.cu", "arena.cu", "trace_kernels.cu", "raygen_kernels.cu", "resolve_kernels.cu", "fp32_peak.cu", "bvh.cu"]
+SOURCES = ["capi.cu", "arena.cu", "trace_kernels.cu", "raygen_kernels.cu", "resolve_kernels.cu", "fp32_peak.cu", "bvh.cu", "multi.cu"]
 HEADERS = ["pt_device.cuh", "pt_material.cuh", "pt_bvh.cuh", "pt_raygen.cuh", "pt_host.h", "philox.h", os.path.join("..", "..", "include", "ptb200.h")]
 
 NVCC_FLAGS = [
@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     # Bit-exactness: no FMA contraction anywhere, IEEE division / square root, denormals kept.
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden",
-    "-rdc=false", "-shared",
+    "-rdc=false", "-shared", "-Xcompiler", "-pthread",
 ]
 
 

@@ -377,23 +377,17 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
                  o_visits = carve(temp_bytes, sizeof(unsigned int) * ns1), o_own = carve(temp_bytes, sizeof(Aabb) * ns1),
                  o_cub = carve(temp_bytes, cub_bytes ? cub_bytes : 16);
     char *keep = nullptr, *temp = nullptr;
-    PtArena *arena = nullptr;
-    bool temp_from_arena = false;
+    WsBlock ws;
     if (e == cudaSuccess)
         e = cudaMalloc(reinterpret_cast<void **>(&keep), keep_bytes);
     if (e == cudaSuccess) {
-        if (workspace(temp_bytes + 256, &arena) == PTB200_OK && (temp = static_cast<char *>(ptb200_arena_alloc(arena, temp_bytes))) != nullptr)
-            temp_from_arena = true;
+        if (ws_alloc(temp_bytes, &ws) == PTB200_OK)
+            temp = static_cast<char *>(ws.ptr);
         else
-            e = cudaMalloc(reinterpret_cast<void **>(&temp), temp_bytes);
+            e = cudaErrorMemoryAllocation;
     }
     auto release_temp = [&] {
-        if (temp == nullptr)
-            return;
-        if (temp_from_arena)
-            ptb200_arena_free(arena, temp);
-        else
-            cudaFree(temp);
+        ws_free(&ws);
         temp = nullptr;
     };
     if (e != cudaSuccess) {

@@ -42,6 +42,8 @@ PtParams g_legacy = {16, 16, 1, 5, 8, 8, 7, 12.0f, 0, 0};  // src/common.h:4-6,1
 
 int64_t total_paths(const PtParams &p) { return static_cast<int64_t>(p.width) * p.height * 4 * p.samples; }
 
+}  // namespace
+
 int check_params(const PtParams *p, const char *who) {
     if (p == nullptr)
         return fail(PTB200_EINVAL, "%s: params is NULL", who);
@@ -66,42 +68,88 @@ int check_device(const char *who) {
     return PTB200_OK;
 }
 
-}  // namespace
+int check_material_params(const PtMaterialParams *mp, const char *who) {
+    if (mp == nullptr)
+        return fail(PTB200_EINVAL, "%s: material params is NULL", who);
+    if (mp->max_depth < 1 || mp->rr_start < 0 || !(mp->hit_epsilon > 0.0f))
+        return fail(PTB200_EINVAL, "%s: need max_depth >= 1, rr_start >= 0, hit_epsilon > 0", who);
+    return PTB200_OK;
+}
 
 // ---- per-device workspace arena (grown on demand) ----------------------------------------------------
 namespace {
+// Per device: a short list of arenas.  One is the normal case; a second (third, ...) appears only when a request does not
+// fit while blocks of the existing ones are held -- by another host thread, or by the caller itself (e.g. the multi-device
+// entry's staging frame while its worker renders).  When every arena is idle and none fits, they are all replaced by one.
 struct Workspace {
-    PtArena *arena = nullptr;
-    size_t capacity = 0;
+    std::vector<PtArena *> arenas;
 };
 Workspace g_ws[64];
 std::mutex g_ws_mu;
+constexpr size_t kMinArena = 256u << 20;  // small requests share one arena instead of each forcing a cudaMalloc
+
+// Environment overrides are for experiments; anything unparsable or below `lo` is ignored.
+long long env_ll(const char *name, long long dflt, long long lo) {
+    const char *e = getenv(name);
+    if (e == nullptr || *e == '\0')
+        return dflt;
+    char *end = nullptr;
+    const long long v = strtoll(e, &end, 10);
+    return (end == e || v < lo) ? dflt : v;
+}
 }  // namespace
 
-// Returns an arena with at least `bytes` free in one block; recreates (after a device sync) when too small.
-int workspace(size_t bytes, PtArena **out) {
+int ws_alloc(size_t bytes, WsBlock *out) {
+    out->ptr = nullptr;
+    out->arena = nullptr;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess)
         return fail_cuda(e, "workspace");
-    std::lock_guard<std::mutex> lock(g_ws_mu);
+    std::lock_guard<std::mutex> lock(g_ws_mu);  // size check and allocation are one critical section
     Workspace &w = g_ws[dev & 63];
-    if (w.arena == nullptr || ptb200_arena_largest_free(w.arena) < bytes) {
-        if (w.arena != nullptr) {
-            if (ptb200_arena_in_use(w.arena) != 0)
-                return fail(PTB200_ENOMEM, "workspace: arena too small (%zu needed) while still in use", bytes);
-            cudaDeviceSynchronize();
-            ptb200_arena_destroy(w.arena);
-            w.arena = nullptr;
+    bool all_idle = true;
+    for (PtArena *a : w.arenas) {
+        if ((out->ptr = ptb200_arena_alloc(a, bytes)) != nullptr) {
+            out->arena = a;
+            return PTB200_OK;
         }
-        const size_t cap = bytes + (bytes >> 3) + (1u << 20);
-        int rc = ptb200_arena_create(cap, &w.arena);
-        if (rc != PTB200_OK)
-            return rc;
-        w.capacity = cap;
+        all_idle = all_idle && ptb200_arena_in_use(a) == 0;
     }
-    *out = w.arena;
+    if (all_idle) {
+        // Nobody holds a block (every user synchronises its streams before ws_free): one larger arena replaces them all.
+        // cudaFree waits for the device by itself; no explicit device-wide synchronisation is added for other tenants.
+        for (PtArena *a : w.arenas)
+            ptb200_arena_destroy(a);
+        w.arenas.clear();
+    }
+    size_t cap = bytes + (bytes >> 3) + (1u << 20);
+    if (cap < kMinArena)
+        cap = kMinArena;
+    PtArena *fresh = nullptr;
+    int rc = ptb200_arena_create(cap, &fresh);
+    if (rc != PTB200_OK && cap > bytes + 4096) {  // a crowded device: retry with exactly what is needed
+        cudaGetLastError();
+        rc = ptb200_arena_create(bytes + 4096, &fresh);
+    }
+    if (rc != PTB200_OK)
+        return rc;
+    w.arenas.push_back(fresh);
+    if ((out->ptr = ptb200_arena_alloc(fresh, bytes)) == nullptr)
+        return PTB200_ENOMEM;
+    out->arena = fresh;
     return PTB200_OK;
+}
+
+void ws_free(WsBlock *b) {
+    if (b == nullptr || b->ptr == nullptr)
+        return;
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mu);  // an arena is never replaced while one of its blocks is counted in use
+        ptb200_arena_free(b->arena, b->ptr);
+    }
+    b->ptr = nullptr;
+    b->arena = nullptr;
 }
 
 }  // namespace ptb200
@@ -226,9 +274,11 @@ int ptb200_resolve(const PtParams *p, void *stream, const float *colors, int32_t
     return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_resolve");
 }
 
-static int render_image_impl(const char *who, const PtParams *p, const PtMaterialParams *mp, void *stream_, const uint8_t *spheres,
-                             const double *uniforms, uint64_t seed, int32_t x0, int32_t x1, int gamma, uint8_t *image, uint64_t *stats,
-                             const PtBvh *tree = nullptr) {
+}  // extern "C"
+
+int ptb200::render_image_impl(const char *who, const PtParams *p, const PtMaterialParams *mp, void *stream_, const uint8_t *spheres,
+                              const double *uniforms, uint64_t seed, int32_t x0, int32_t x1, int gamma, uint8_t *image, uint64_t *stats,
+                              const PtBvh *tree) {
     int rc = check_params(p, who);
     if (rc != PTB200_OK)
         return rc;
@@ -259,16 +309,12 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
     // ends in a tail in which all warps run out of fresh paths at about the same time and finish their last ones with
     // ever fewer lanes busy: ~0.1 ms for the mirror kernel but 4-8 ms for the BVH material kernel (paths of up to 64
     // bounces; profiles/r1_c4_tail.md), so a frame should be as few launches as memory allows.  PTB200_TILE_PATHS overrides.
-    static const int64_t target_paths = [] {
-        const char *e = getenv("PTB200_TILE_PATHS");
-        const long long v = e ? atoll(e) : 0;
-        return v > 0 ? static_cast<int64_t>(v) : (512LL << 20);
-    }();
+    static const int64_t target_paths = env_ll("PTB200_TILE_PATHS", 512LL << 20, 1024);
     // Rays are generated inside the trace kernel (straight into its shared-memory ring) and never exist in HBM; only the
     // per-path colours of a tile (12 B/path) are materialised between the trace and the resolve kernel.  If the device
     // cannot spare the workspace (other tenants, a smaller GPU) the tile is halved until it fits, down to 16 Mi paths.
-    PtArena *arena = nullptr;
-    float *rays = nullptr, *cols = nullptr;
+    WsBlock ws;
+    float *cols = nullptr;
     int64_t tile_pix = 0;
     for (int64_t want = target_paths;; want /= 2) {
         tile_pix = want / spp;
@@ -277,12 +323,10 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
         if (tile_pix > pix_end - pix_begin)
             tile_pix = pix_end - pix_begin;
         const size_t col_bytes = sizeof(float) * 3 * static_cast<size_t>(tile_pix * spp);
-        rc = workspace(col_bytes + 4096, &arena);
+        rc = ws_alloc(col_bytes, &ws);
         if (rc == PTB200_OK) {
-            cols = static_cast<float *>(ptb200_arena_alloc(arena, col_bytes));
-            if (cols != nullptr)
-                break;
-            rc = PTB200_ENOMEM;
+            cols = static_cast<float *>(ws.ptr);
+            break;
         }
         if (rc != PTB200_ENOMEM || want <= (16LL << 20) || tile_pix * spp <= (16LL << 20))
             return rc;
@@ -320,24 +364,17 @@ static int render_image_impl(const char *who, const PtParams *p, const PtMateria
         e = cudaMemcpyAsync(stats, &total, sizeof total, cudaMemcpyHostToDevice, stream);  // drained by the sync below
     // Stream-ordered reuse: the buffers go back to the arena once the work queued above has drained.
     cudaError_t es = cudaStreamSynchronize(stream);
-    ptb200_arena_free(arena, rays);
-    ptb200_arena_free(arena, cols);
+    ws_free(&ws);
     if (e == cudaSuccess)
         e = es;
     return e == cudaSuccess ? PTB200_OK : fail_cuda(e, who);
 }
 
+extern "C" {
+
 int ptb200_render_image(const PtParams *p, void *stream, const uint8_t *spheres, const double *uniforms, uint64_t seed, int32_t x0,
                         int32_t x1, uint8_t *image, uint64_t *stats) {
     return render_image_impl("ptb200_render_image", p, nullptr, stream, spheres, uniforms, seed, x0, x1, 0, image, stats);
-}
-
-static int check_material_params(const PtMaterialParams *mp, const char *who) {
-    if (mp == nullptr)
-        return fail(PTB200_EINVAL, "%s: material params is NULL", who);
-    if (mp->max_depth < 1 || mp->rr_start < 0 || !(mp->hit_epsilon > 0.0f))
-        return fail(PTB200_EINVAL, "%s: need max_depth >= 1, rr_start >= 0, hit_epsilon > 0", who);
-    return PTB200_OK;
 }
 
 int ptb200_render_image_mat(const PtParams *p, const PtMaterialParams *mp, void *stream, const uint8_t *spheres, uint64_t cam_seed, int32_t x0,
@@ -475,23 +512,39 @@ int ptb200_smallpt_scene(float *out) {
 }
 
 int ptb200_render_host(const PtParams *p, const float *rays_host, const float *spheres_host, float *colors_host) {
-    int rc = check_params(p, "ptb200_render_host");
+    return render_host_slice("ptb200_render_host", p, rays_host, spheres_host, colors_host, 0, -1);
+}
+
+}  // extern "C"
+
+// Paths [first, first+count) of the N-path HOST buffers on the CURRENT device (the whole job, or one device's share of it:
+// the reference's per-core slice, src/render.cpp:24-27).
+int ptb200::render_host_slice(const char *who, const PtParams *p, const float *rays_host, const float *spheres_host, float *colors_host, int64_t first,
+                              int64_t count) {
+    int rc = check_params(p, who);
     if (rc != PTB200_OK)
         return rc;
     if (rays_host == nullptr || spheres_host == nullptr || colors_host == nullptr)
-        return fail(PTB200_EINVAL, "ptb200_render_host: NULL buffer");
-    if ((rc = check_device("ptb200_render_host")) != PTB200_OK)
+        return fail(PTB200_EINVAL, "%s: NULL buffer", who);
+    if ((rc = check_device(who)) != PTB200_OK)
         return rc;
-    const int64_t n = total_paths(*p);
+    const int64_t n_total = total_paths(*p);
+    if (count < 0)
+        count = n_total - first;
+    if (first < 0 || first + count > n_total)
+        return fail(PTB200_EINVAL, "%s: slice [%lld, %lld) outside [0, %lld)", who, static_cast<long long>(first), static_cast<long long>(first + count),
+                    static_cast<long long>(n_total));
+    if (count == 0)
+        return PTB200_OK;
+    const int64_t n = count;  // the job of this call
+    rays_host += first;       // plane c of the slice starts at rays_host + c * n_total
+    colors_host += first;
     const size_t sph_bytes = sizeof(float) * 10 * static_cast<size_t>(p->sphere_stride);
     const size_t sph_alloc = sph_bytes < 512 ? 512 : sph_bytes;
     // Chunked so that the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap
     // (three engines, three streams).  With pinned host memory the copies are truly asynchronous.
     constexpr int kStreams = 4;
-    static const int64_t chunk_paths = [] {  // PTB200_HOST_CHUNK overrides (experiments)
-        const char *e = getenv("PTB200_HOST_CHUNK");
-        return e ? atoll(e) : (8LL << 20);
-    }();
+    static const int64_t chunk_paths = env_ll("PTB200_HOST_CHUNK", 8LL << 20, 1024);  // experiments only; below 1024 is ignored
     // Peak paths per chunk: 192 MiB in, 96 MiB out.  Measured on C2 (1.2 GB in, 0.6 GB out) with the ramped schedule below:
     // 4 Mi 25.9 ms, 8 Mi 25.1, 16 Mi 25.0, 32 Mi 25.1; equal 4 Mi chunks without the ramps 26.7 ms.  The link itself moves
     // the same bytes in 23.0 ms as two giant copies (52.5 GB/s in while 26.3 GB/s go out, tools/pcie_probe.py).
@@ -499,19 +552,20 @@ int ptb200_render_host(const PtParams *p, const float *rays_host, const float *s
     if (chunk > n)
         chunk = n;
     const int nbuf = static_cast<int>((n + chunk - 1) / chunk < kStreams ? (n + chunk - 1) / chunk : kStreams);
-    PtArena *arena = nullptr;
-    const size_t per_buf = sizeof(float) * 9 * static_cast<size_t>(chunk) + 1024;
-    if ((rc = workspace(per_buf * nbuf + sph_alloc + 4096, &arena)) != PTB200_OK)
+    // one workspace block, carved by hand: [spheres | staging buffer 0 | ... | staging buffer nbuf-1], 256-byte aligned pieces
+    const size_t per_buf = (sizeof(float) * 9 * static_cast<size_t>(chunk) + 1023) & ~static_cast<size_t>(255);
+    const size_t sph_piece = (sph_alloc + 255) & ~static_cast<size_t>(255);
+    WsBlock ws;
+    if ((rc = ws_alloc(per_buf * nbuf + sph_piece, &ws)) != PTB200_OK)
         return rc;
-    float *d_sph = static_cast<float *>(ptb200_arena_alloc(arena, sph_alloc));
+    float *d_sph = static_cast<float *>(ws.ptr);
     float *d_buf[kStreams] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr, nullptr};
     cudaError_t e = cudaSuccess;
-    bool ok = d_sph != nullptr;
+    bool ok = true;
     for (int b = 0; b < nbuf && ok; b++) {
-        d_buf[b] = static_cast<float *>(ptb200_arena_alloc(arena, per_buf));
-        ok = d_buf[b] != nullptr;
-        if (ok && (e = cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking)) != cudaSuccess)
+        d_buf[b] = reinterpret_cast<float *>(static_cast<char *>(ws.ptr) + sph_piece + per_buf * b);
+        if ((e = cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking)) != cudaSuccess)
             ok = false;
     }
     cudaEvent_t sph_ready = nullptr;
@@ -553,11 +607,11 @@ int ptb200_render_host(const PtParams *p, const float *rays_host, const float *s
             const int b = k % nbuf;
             float *d_rays = d_buf[b], *d_cols = d_buf[b] + 6 * chunk;
             for (int c = 0; c < 6 && e == cudaSuccess; c++)
-                e = cudaMemcpyAsync(d_rays + c * m, rays_host + c * n + a, sizeof(float) * m, cudaMemcpyHostToDevice, st[b]);
+                e = cudaMemcpyAsync(d_rays + c * m, rays_host + c * n_total + a, sizeof(float) * m, cudaMemcpyHostToDevice, st[b]);
             if (e == cudaSuccess)
                 e = trace_paths(st[b], cp, d_rays, d_sph, d_cols, m, 0, m, nullptr);
             for (int c = 0; c < 3 && e == cudaSuccess; c++)
-                e = cudaMemcpyAsync(colors_host + c * n + a, d_cols + c * m, sizeof(float) * m, cudaMemcpyDeviceToHost, st[b]);
+                e = cudaMemcpyAsync(colors_host + c * n_total + a, d_cols + c * m, sizeof(float) * m, cudaMemcpyDeviceToHost, st[b]);
         }
     }
     for (int b = 0; b < nbuf; b++)
@@ -569,13 +623,13 @@ int ptb200_render_host(const PtParams *p, const float *rays_host, const float *s
         }
     if (sph_ready != nullptr)
         cudaEventDestroy(sph_ready);
-    ptb200_arena_free(arena, d_sph);
-    for (int b = 0; b < nbuf; b++)
-        ptb200_arena_free(arena, d_buf[b]);
+    ws_free(&ws);
     if (!ok && e == cudaSuccess)
         return PTB200_ENOMEM;
-    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, "ptb200_render_host");
+    return e == cudaSuccess ? PTB200_OK : fail_cuda(e, who);
 }
+
+extern "C" {
 
 // ---- host helpers -------------------------------------------------------------------------------------
 

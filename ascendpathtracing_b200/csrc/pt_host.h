@@ -46,9 +46,27 @@ cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *
 // fp32_peak.cu
 cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms);
 
-// capi.cu -- the per-device workspace arena (csrc/arena.cu), grown on demand: an arena with at least `bytes` free in one
-// block.  Fails with PTB200_ENOMEM when it would have to grow while blocks are still in use.
-int workspace(size_t bytes, PtArena **out);
+// capi.cu -- the per-device workspace arenas (csrc/arena.cu), grown on demand.  ws_alloc hands out ONE block of `bytes`
+// (256-byte aligned) from an arena that can serve it; when none can, all arenas are replaced by a larger one if nobody holds
+// a block, otherwise (another host thread, or the caller itself, is using them) an additional arena is created.  The size
+// check and the allocation happen under one lock, so concurrent callers on one device never see each other's arena die.
+struct WsBlock {
+    void *ptr = nullptr;
+    PtArena *arena = nullptr;  // the arena the block came from
+};
+int ws_alloc(size_t bytes, WsBlock *out);
+void ws_free(WsBlock *b);  // the caller has synchronised every stream that touched the block
+
+// capi.cu -- the bodies of ptb200_render_image* and ptb200_render_host, shared with the multi-device entries (multi.cu)
+int render_image_impl(const char *who, const PtParams *p, const PtMaterialParams *mp, void *stream, const uint8_t *spheres, const double *uniforms,
+                      uint64_t seed, int32_t x0, int32_t x1, int gamma, uint8_t *image, uint64_t *stats, const PtBvh *tree = nullptr);
+int render_host_slice(const char *who, const PtParams *p, const float *rays_host, const float *spheres_host, float *colors_host, int64_t first,
+                      int64_t count);
+
+// argument validation (capi.cu); every failure sets the thread-local error text
+int check_params(const PtParams *p, const char *who);
+int check_material_params(const PtMaterialParams *mp, const char *who);
+int check_device(const char *who);
 
 // error plumbing (capi.cu)
 int fail(int code, const char *fmt, ...);

@@ -619,6 +619,7 @@ namespace {
 
 struct DeviceState {
     bool init = false;
+    int device = 0;
     int sm_count = 0;
     int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [GEN?][NS8?][EARLY?]
     SceneConst *scene_alias = nullptr;
@@ -661,10 +662,24 @@ cudaError_t ensure_device_state(DeviceState **out) {
             return e;
         if ((e = cudaMalloc(reinterpret_cast<void **>(&s.work_counter), sizeof(unsigned long long))) != cudaSuccess)
             return e;
+        s.device = dev;
         s.init = true;
     }
     *out = &s;
     return cudaSuccess;
+}
+
+// The staged scene, the generator block and the chunk dispenser belong to the CURRENT device: a stream of another device
+// would run the kernels there against this device's staging.  Refused instead of silently misbehaving.
+cudaError_t check_stream_device(const DeviceState &s, cudaStream_t stream) {
+    if (stream == nullptr || stream == cudaStreamLegacy || stream == cudaStreamPerThread)
+        return cudaSuccess;
+    int sd = -1;
+    if (cudaStreamGetDevice(stream, &sd) != cudaSuccess) {
+        cudaGetLastError();
+        return cudaErrorInvalidResourceHandle;
+    }
+    return sd == s.device ? cudaSuccess : cudaErrorInvalidDevice;
 }
 
 template <int NS, bool EARLY, bool GEN>
@@ -673,11 +688,16 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
     const size_t smem = sizeof(float4) * 2 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
     int &occ = s.blocks_per_sm[(GEN ? 4 : 0) + (NS > 0 ? 2 : 0) + (EARLY ? 1 : 0)];
     if (occ == 0 || NS == 0) {
-        cudaError_t e = occupancy<NS, EARLY, GEN>(&occ, smem);
-        if (e != cudaSuccess)
+        cudaError_t e = cudaSuccess;
+        if (smem > 48 * 1024 &&  // 769..1024 spheres: opt in to more than the default 48 KB of dynamic shared memory
+            (e = cudaFuncSetAttribute(trace_paths_kernel<NS, EARLY, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
             return e;
-        if (occ < 1)
-            occ = 1;
+        if ((e = occupancy<NS, EARLY, GEN>(&occ, smem)) != cudaSuccess)
+            return e;
+        if (occ < 1) {  // the kernel cannot be resident at all with this much shared memory: fail loudly, do not guess a grid
+            occ = 0;
+            return cudaErrorLaunchOutOfResources;
+        }
     }
     const int64_t cap = static_cast<int64_t>(s.sm_count) * occ;
     constexpr int64_t kMaxPerLaunch = 1LL << 30;  // 32-bit path indices inside the kernel
@@ -719,7 +739,7 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
     std::lock_guard<std::mutex> lock(g_mu);
     DeviceState *s = nullptr;
     cudaError_t e = ensure_device_state(&s);
-    if (e != cudaSuccess)
+    if (e != cudaSuccess || (e = check_stream_device(*s, stream)) != cudaSuccess)
         return e;
     // The constant-bank scene is a per-device singleton: a launch sequence on another stream must
     // wait until the previous sequence has finished reading it.
@@ -735,9 +755,10 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
     // (103-109 Gsegments/s) but they skip the settled part of every path: 21 % of the segments at depth 5, 13 % at depth 4.
     // Measured on B200 (tools/early_crossover.py, 132.7 M paths): depth 3: 3.72 vs 3.50 ms (lock step wins), depth 4: 4.52 vs
     // 4.54 (a tie), depth 5: 5.08 vs 5.58, depth 6: 5.56 vs 6.62, depth 50: 18.6 vs 100.8 -> regeneration from depth 5 on.
-    static const int min_early_depth = [] {  // PTB200_EARLY_FROM_DEPTH overrides the crossover (experiments)
+    static const int min_early_depth = [] {  // PTB200_EARLY_FROM_DEPTH overrides the crossover (experiments); values < 1 are ignored
         const char *e = getenv("PTB200_EARLY_FROM_DEPTH");
-        return e ? atoi(e) : 5;
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 ? v : 5;
     }();
     const bool early = !(p.flags & PTB200_F_FIXED_DEPTH) && p.depth >= min_early_depth;
     if (p.sphere_count == 8)
@@ -778,7 +799,7 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
     std::lock_guard<std::mutex> lock(g_mu);
     DeviceState *s = nullptr;
     cudaError_t e = ensure_device_state(&s);
-    if (e != cudaSuccess)
+    if (e != cudaSuccess || (e = check_stream_device(*s, stream)) != cudaSuccess)
         return e;
     if (s->have_last && s->last_stream != stream) {
         if ((e = cudaStreamWaitEvent(stream, s->scene_free, 0)) != cudaSuccess)
@@ -798,14 +819,19 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
             (e = cudaFuncSetAttribute(trace_materials_bvh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
             return e;
     }
+    if (!use_tree && !ten && smem > 48 * 1024) {  // 513..1024 spheres: opt in to more than the default 48 KB of dynamic shared memory
+        if ((e = cudaFuncSetAttribute(trace_materials_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess ||
+            (e = cudaFuncSetAttribute(trace_materials_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+            return e;
+    }
     int occ = 0;
     // the fused-generation variants have the same resource footprint as the SoA ones (the generator is an out-of-line call)
     if ((e = use_tree ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_bvh_kernel<false>, kTraceThreads, smem)
               : ten   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<10, false>, kTraceThreads, smem)
                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_materials_kernel<0, false>, kTraceThreads, smem)) != cudaSuccess)
         return e;
-    if (occ < 1)
-        occ = 1;
+    if (occ < 1)  // cannot be resident at all: fail loudly instead of guessing a grid
+        return cudaErrorLaunchOutOfResources;
     const int64_t cap = static_cast<int64_t>(s->sm_count) * occ;
     constexpr int64_t kMaxPerLaunch = 1LL << 30;
     for (int64_t a = first; a < first + count; a += kMaxPerLaunch) {

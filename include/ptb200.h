@@ -6,6 +6,14 @@
  * (a cudaStream_t passed as void*, NULL = the legacy default stream) exactly like the reference's
  * render_do (src/render.cpp:264-266; the caller synchronises, src/main.cpp:75).
  *
+ * Threads and streams: every entry may be called from several host threads at once (the last-error text is per thread; the
+ * library's workspace arenas hand out blocks under one lock and grow by adding an arena while blocks are held).  `stream`
+ * must belong to the CURRENT device (checked: cudaErrorInvalidDevice otherwise).  On one device the trace launches of
+ * different streams run ONE AFTER THE OTHER, not side by side: the staged scene (constant bank), the ray-generator block
+ * and the chunk dispenser of the persistent kernels are per-device singletons, and a launch sequence waits on an event for
+ * the previous one to finish reading them.  Streams therefore overlap copies and resolves with a trace, never two traces --
+ * one trace launch already fills all 148 SMs.  Different devices are fully independent.
+ *
  * Return values: 0 on success, otherwise a negative PTB200_E* code or a positive cudaError_t.
  * ptb200_last_error() returns a thread-local human-readable message for the last failure.
  * There is no CPU fallback anywhere: without a CUDA device every compute entry fails with
@@ -29,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PTB200_ABI_VERSION 1
+#define PTB200_ABI_VERSION 2
 
 /* exported from libptb200.so (the library is built with -fvisibility=hidden) */
 #if defined(__GNUC__)
@@ -192,6 +200,48 @@ PTB200_API int ptb200_random_scene(int32_t n_random, uint32_t seed, int32_t stri
 /* HOST buffers in, HOST buffer out: arena allocation, H2D of rays+spheres, render, D2H of colours,
  * synchronous.  This is the end-to-end call bench.py times. */
 PTB200_API int ptb200_render_host(const PtParams *p, const float *rays_host, const float *spheres_host, float *colors_host);
+
+/* ---- one process, several GPUs (the reference's 8-way split, src/render.cpp:9-10,24-27) -------------- */
+
+/* The reference's kernel owns an 8-way split of the flat path array (blockDim = 8 AI cores, contiguous slices); its host
+ * owns device selection, stream, copies, launch and synchronisation (src/main.cpp:46-92).  The two entries below are that
+ * host for n_devices GPUs of one box: one host thread and one stream per device, the scene replicated, no exchange while
+ * rendering.  devices == NULL means 0 .. n_devices-1; 1 <= n_devices <= 16; the caller's current device is restored.
+ * A device may be listed more than once (its shares then run one after the other on it).
+ *
+ * ptb200_render_host_multi: ptb200_render_host with the N paths cut into n_devices contiguous slices (device r gets
+ * [r*N/n, (r+1)*N/n), exactly the reference's per-core rule); every device streams its slice of the HOST ray planes in and
+ * its slice of the HOST colour planes out.  Pinned host buffers (cudaMallocHost / cudaHostRegister) make the copies overlap.
+ * ms_host (nullable, 1 + n_devices doubles): wall milliseconds of the call, then of every device's slice. */
+PTB200_API int ptb200_render_host_multi(const PtParams *p, const int32_t *devices, int32_t n_devices, const float *rays_host,
+                                        const float *spheres_host, float *colors_host, double *ms_host);
+
+/* ptb200_render_image_multi: the production composition (generate, trace, resolve) of the whole W x H frame on n_devices
+ * GPUs.  Device r renders image columns r, r + n, r + 2n, ... in ONE launch sequence (PtParams.column_step, which this entry
+ * sets itself), so every GPU sees the same mix of cheap and expensive columns; the 8-bit column sets are then gathered on
+ * devices[0] over NVLink (cudaMemcpyPeerAsync, peer access enabled once per pair), interleaved into the [H][W][3] frame by a
+ * small kernel there and copied to `image`, which may be HOST memory or memory of devices[0].  Random numbers are keyed by
+ * the global path index, so the frame is bit-identical for every n_devices (tests).
+ *   mp == NULL: the reference-parity mirror kernel (spheres_host = SoA [10][stride]); otherwise the material extension
+ *   (SoA [11][stride]); use_bvh != 0 (needs mp) builds the sphere BVH on every device first (scenes beyond 1024 spheres).
+ *   seed: counter-based camera RNG key.  gamma as in ptb200_render_image_mat.
+ *   stats_host (nullable, 2 uint64): paths traced, ray segments traced, summed over the devices.
+ *   ms_host (nullable, 1 + n_devices doubles): wall milliseconds of the call (scene upload to image in place), then each
+ *   device's own share (upload, BVH build, render, peer copy). */
+PTB200_API int ptb200_render_image_multi(const PtParams *p, const PtMaterialParams *mp, int32_t use_bvh, int32_t gamma, const int32_t *devices,
+                                         int32_t n_devices, const float *spheres_host, uint64_t seed, uint8_t *image, uint64_t *stats_host,
+                                         double *ms_host);
+
+/* ---- scene files beyond the reference's 512 bytes ------------------------------------------------ */
+
+/* HOST helper: the layout of an input/spheres.bin of `bytes` bytes.
+ *   512 bytes            the reference's file (src/main.cpp:24, scripts/gen_data.py:120-127): SoA [10][8] + 48 zero floats;
+ *                        count = stride = 8 (SPHERE_NUM, src/common.h:10).  Read as an 11-row scene its material row is the
+ *                        zero padding: every sphere DIFF.
+ *   44 * stride bytes    SoA [11][stride]: the reference's ten rows (src/rt_helper.h:91-103) + material (0 DIFF, 1 SPEC,
+ *                        2 REFR); count = stride minus trailing columns whose r^2 is 0 (padding), at least 1.
+ * Anything else is PTB200_EINVAL.  `scene_host` may be NULL when only the stride is wanted (count is then = stride). */
+PTB200_API int ptb200_scene_layout(const float *scene_host, size_t bytes, int32_t *count, int32_t *stride, int32_t *rows);
 
 /* ---- device arena: replaces src/allocator.h's MemoryPool for the big buffers -------------------- */
 

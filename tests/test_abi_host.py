@@ -21,7 +21,23 @@ def test_library_exports_every_declared_symbol(pt):
     # nothing but the declared ABI leaks out of the library
     leaked = {s for s in exported if not s.startswith("_")} - set(pt.ABI_SYMBOLS)
     assert not leaked, leaked
-    assert L.ptb200_abi_version() == 1
+    assert L.ptb200_abi_version() == 2  # round 2: + the multi-device entries and ptb200_scene_layout
+
+
+def test_scene_file_layout_is_derived_from_its_size(pt):
+    """input/spheres.bin beyond the reference's 512 bytes: 512 = the reference's own file, byte
+    compatible (count = stride = 8, src/main.cpp:24, common.h:10); otherwise whole 44-byte columns of the 11-row SoA with the
+    trailing zero-radius columns counted as padding; anything else is refused."""
+    assert pt.scene_layout(512) == (8, 8, 11)
+    assert pt.scene_layout(512, pt.default_scene()) == (8, 8, 11)
+    assert pt.scene_layout(44 * 16, pt.smallpt_scene()) == (9, 16, 11)
+    assert pt.scene_layout(44 * 16) == (16, 16, 11)            # without the contents only the stride is known
+    big = pt.random_scene(100, stride=128)
+    assert pt.scene_layout(big.nbytes, big) == (107, 128, 11)
+    assert pt.scene_layout(44 * 107, pt.random_scene(100)) == (107, 107, 11)
+    for bad in (0, 100, 511, 513, 40 * 8):
+        with pytest.raises(pt.PtError):
+            pt.scene_layout(bad)
 
 
 def test_library_is_built_for_sm_100a_only(pt):
