@@ -145,10 +145,15 @@ int main(int argc, char **argv) {
         ERROR_LOG("no CUDA device: the B200 build has no CPU fallback (use run.sh -r cpu for the reference's cpu mode)");
         return 1;
     }
-    if (n_dev < 1 || n_dev > ptb200_device_count()) {
-        ERROR_LOG("%d GPUs requested, %d visible", n_dev, ptb200_device_count());
+    if (n_dev < 1 || n_dev > 16) {
+        ERROR_LOG("%d GPUs requested: 1 to 16 supported", n_dev);
         return 1;
     }
+    for (int32_t d : devices)  // (a device may be listed more than once with --devices: its shares then run one after the other)
+        if (d < 0 || d >= ptb200_device_count()) {
+            ERROR_LOG("GPU %d requested, %d visible", d, ptb200_device_count());
+            return 1;
+        }
     if (use_bvh && !materials) {
         ERROR_LOG("--bvh is the material kernel's scene representation: add --materials");
         return 1;

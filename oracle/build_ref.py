@@ -43,6 +43,12 @@ DEFAULT_CONFIGS = [
     (64, 64, 1, 50),
     (1024, 1024, 1, 5), # 4 194 304 paths: bounded sample of C2 for the reference arm at many steps
     (1024, 768, 4, 5),  # 12 582 912 paths: the C2 frame at 16 spp, the CPU baseline's sample (~18 s of CPU work)
+    (1024, 768, 16, 5), # 50 331 648 paths: BASELINE config C2 itself, what `bench.py --impl reference` times per step
+]
+# The reference's own cpu-mode flags are `-g` alone, i.e. -O0 (cmake/cpu/CMakeLists.txt:26-28); BASELINE.md section 3 asks for that
+# variant next to -O2.  Same bits either way (tests), very different speed.
+REFERENCE_FLAGS_CONFIGS = [
+    (256, 256, 1, 5),   # the survey's probe size: -O0 single thread ~3 s
 ]
 
 
@@ -54,17 +60,21 @@ def have_reference():
     return os.path.isfile(os.path.join(REF_SRC, "render.cpp"))
 
 
-def lib_path(w, h, s, d=5):
-    return os.path.join(OUT, f"libref_{tag(w, h, s, d)}.so")
+def _suffix(opt):
+    return "" if opt == "-O2" else "_O0g"   # "_O0g" = the reference's own flags: -g, no optimisation
 
 
-def bin_path(w, h, s, d=5):
-    return os.path.join(OUT, f"render_cpu_{tag(w, h, s, d)}")
+def lib_path(w, h, s, d=5, opt="-O2"):
+    return os.path.join(OUT, f"libref_{tag(w, h, s, d)}{_suffix(opt)}.so")
+
+
+def bin_path(w, h, s, d=5, opt="-O2"):
+    return os.path.join(OUT, f"render_cpu_{tag(w, h, s, d)}{_suffix(opt)}")
 
 
 def build(w, h, s, d=5, force=False, opt="-O2"):
-    """Build both artefacts for one configuration; returns (lib, bin)."""
-    lib, exe = lib_path(w, h, s, d), bin_path(w, h, s, d)
+    """Build both artefacts for one configuration; returns (lib, bin).  opt: "-O2" (default) or "-O0" (+ -g: the reference's own flags)."""
+    lib, exe = lib_path(w, h, s, d, opt), bin_path(w, h, s, d, opt)
     if not force and os.path.isfile(lib) and os.path.isfile(exe):
         return lib, exe
     if not have_reference():
@@ -92,7 +102,7 @@ def build(w, h, s, d=5, force=False, opt="-O2"):
                     "const float PI = 3.1415926535897932385f;\nconstexpr float EPSILON = 1e-4;\n"
                     "const int32_t SPHERE_NUM = 8;\nconst int32_t SPHERE_MEMBER_NUM = 10;\nusing Float = float;\n"
                     "const int32_t GENERIC_SIZE = 64;\n")
-        flags = [f for f in CXXFLAGS if f != "-O2"] + [opt, f"-I{tmp}", f"-I{SHIM}"]
+        flags = [f for f in CXXFLAGS if f != "-O2"] + ([opt] if opt == "-O2" else ["-O0", "-g"]) + [f"-I{tmp}", f"-I{SHIM}"]
         subprocess.check_call(["g++", *flags, os.path.join(tmp, "main.cpp"), os.path.join(tmp, "render.cpp"), "-o", exe])
         subprocess.check_call(["g++", *flags, "-fPIC", "-shared", os.path.join(tmp, "render.cpp"),
                                os.path.join(HERE, "ref_driver.cpp"), "-o", lib])
@@ -111,6 +121,10 @@ def build_all(force=False, verbose=False):
         built.append(build(*cfg, force=force))
         if verbose:
             print("[build_ref]", tag(*cfg), "ok")
+    for cfg in REFERENCE_FLAGS_CONFIGS:
+        built.append(build(*cfg, force=force, opt="-O0"))
+        if verbose:
+            print("[build_ref]", tag(*cfg), "-O0 -g ok")
     return built
 
 

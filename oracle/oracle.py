@@ -206,16 +206,16 @@ def write_ppm(path, img):
 _ref_libs = {}
 
 
-def ref_available(w, h, s, depth=5):
-    return os.path.isfile(_build_ref.lib_path(w, h, s, depth)) or _build_ref.have_reference()
+def ref_available(w, h, s, depth=5, opt="-O2"):
+    return os.path.isfile(_build_ref.lib_path(w, h, s, depth, opt)) or _build_ref.have_reference()
 
 
-def ref_lib(w, h, s, depth=5):
-    key = (w, h, s, depth)
+def ref_lib(w, h, s, depth=5, opt="-O2"):
+    key = (w, h, s, depth, opt)
     if key not in _ref_libs:
-        path = _build_ref.lib_path(w, h, s, depth)
+        path = _build_ref.lib_path(w, h, s, depth, opt)
         if not os.path.isfile(path):
-            _build_ref.build(w, h, s, depth)
+            _build_ref.build(w, h, s, depth, opt=opt)
         L = ctypes.CDLL(path)
         L.ref_render.restype = None
         L.ref_render.argtypes = [_u8p, _u8p, _u8p, ctypes.c_int32]
@@ -228,7 +228,7 @@ def ref_lib(w, h, s, depth=5):
     return _ref_libs[key]
 
 
-def ref_render(rays, spheres, w, h, s, depth=5, threads=1):
+def ref_render(rays, spheres, w, h, s, depth=5, threads=1, opt="-O2"):
     """Run the reference's own `render` (src/render.cpp:253) over its 8 block slices. Returns colors [3, N]."""
     n = w * h * s * 4
     rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1)
@@ -236,5 +236,5 @@ def ref_render(rays, spheres, w, h, s, depth=5, threads=1):
     sp = np.zeros(128, dtype=np.float32)
     sp[:] = np.asarray(spheres, dtype=np.float32).reshape(-1)[:128]
     colors = np.zeros(3 * n, dtype=np.float32)
-    ref_lib(w, h, s, depth).ref_render(rays.view(np.uint8), sp.view(np.uint8), colors.view(np.uint8), threads)
+    ref_lib(w, h, s, depth, opt).ref_render(rays.view(np.uint8), sp.view(np.uint8), colors.view(np.uint8), threads)
     return colors.reshape(3, n)
