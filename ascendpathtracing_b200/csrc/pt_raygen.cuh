@@ -49,6 +49,7 @@ struct RayGenSource {
     RayGenArgs a;
     const double *uniforms;
     unsigned long long seed;
+    PhiloxKeys keys;       // the round keys of `seed` (host-computed: no key-schedule instructions per ray)
     long long path0;
     int fast_index;        // path0 is a whole number of pixels and all indices fit 32 bits
     unsigned int pix_base; // path0 / (4*S) when fast_index
@@ -100,6 +101,7 @@ inline RayGenSource make_raygen_source(const PtParams &p, const double *uniforms
     g.a.by_h = make_fastdiv(static_cast<unsigned int>(p.height));
     g.uniforms = uniforms;
     g.seed = seed;
+    g.keys = philox_keys(seed);
     g.path0 = path0;
     g.fast_index = (path0 % spp == 0) && m < (1LL << 31) && (path0 + m) / spp < (1LL << 31);
     g.pix_base = g.fast_index ? static_cast<unsigned int>(path0 / spp) : 0u;
@@ -133,9 +135,8 @@ __device__ __forceinline__ unsigned long long strided_global_path(const RayGenSo
     return (x * static_cast<unsigned int>(a.ih) + y) * spp + (i - lp * spp);
 }
 
-// tent filter, gen_data.py:37-40: one square root per call (both branches take the root of a value in [0, 1])
-__device__ __forceinline__ double raygen_tent(double u) {
-    const double r = __dmul_rn(2.0, u);
+// tent filter, gen_data.py:37-40, of r = 2 * rand(): one square root per call (both branches take the root of a value in [0, 1])
+__device__ __forceinline__ double raygen_tent(double r) {
     const bool lo = r < 1.0;
     const double sq = __dsqrt_rn(lo ? r : __dsub_rn(2.0, r));
     return lo ? __dsub_rn(sq, 1.0) : __dsub_rn(1.0, sq);
@@ -175,23 +176,35 @@ __device__ __forceinline__ void generate_ray(const RayGenSource &g, long long i,
         y = static_cast<int>(r % a.ih);
         x = static_cast<int>(r / a.ih);
     }
-    double u1, u2;
+    double r1, r2;  // 2 * rand(), gen_data.py:37,39
     if (g.uniforms != nullptr) {
-        u1 = g.uniforms[2 * i];
-        u2 = g.uniforms[2 * i + 1];
+        r1 = __dmul_rn(2.0, g.uniforms[2 * i]);
+        r2 = __dmul_rn(2.0, g.uniforms[2 * i + 1]);
     } else {
+        // rand() = ((a >> 5) * 2^26 + (b >> 6)) / 2^53 = m / 2^53 with the 53-bit integer m = (a >> 5) << 26 | (b >> 6): the sum
+        // and the division are exact in binary64, and so is the doubling: 2 * rand() = m * 2^-52.  One integer conversion and
+        // one exact scaling replace two conversions, a multiply, an add, a divide and the doubling -- same bits.
         const uint64_t gp = g.x_step > 1 ? strided_global_path(g, static_cast<unsigned int>(i)) : static_cast<uint64_t>(g.path0 + i);
-        philox_uniform2(g.seed, gp, u1, u2);
+        uint32_t c[4] = {static_cast<uint32_t>(gp), static_cast<uint32_t>(gp >> 32), 0u, 0u};
+        philox4x32_10_keyed(c, g.keys);
+        const unsigned long long m1 = (static_cast<unsigned long long>(c[0] >> 5) << 26) | (c[1] >> 6);
+        const unsigned long long m2 = (static_cast<unsigned long long>(c[2] >> 5) << 26) | (c[3] >> 6);
+        r1 = __dmul_rn(__ull2double_rn(m1), 0x1p-52);
+        r2 = __dmul_rn(__ull2double_rn(m2), 0x1p-52);
     }
-    const double dx = raygen_tent(u1);
-    const double dy = raygen_tent(u2);
+    const double dx = raygen_tent(r1);
+    const double dy = raygen_tent(r2);
     // ((sx + 0.5 + dx) / 2 + x) / w - 0.5, gen_data.py:41-43  (/2 is an exact scaling)
     const double fx = __dsub_rn(raygen_div_by(__dadd_rn(__dmul_rn(__dadd_rn(sx + 0.5, dx), 0.5), static_cast<double>(x)), a.w, a.rw), 0.5);
     const double fy = __dsub_rn(raygen_div_by(__dadd_rn(__dmul_rn(__dadd_rn(sy + 0.5, dy), 0.5), static_cast<double>(y)), a.h, a.rh), 0.5);
+    // d = cx * fx + cy * fy + dir (gen_data.py:41-43) for THIS camera: cx = (cx0, +0, +0), cy = (+0, cy1, cy2), dir = (+0, d1, d2)
+    // (make_camera; the zeros are exact, cy1 > 0).  The products with those zeros are signed zeros and adding a zero changes no
+    // non-zero value; when the surviving term is itself zero (fx or fy exactly +0, the only zero a "q - 0.5" can round to) every
+    // variant of the sum is +0.  So the three components reduce, bit for bit, to:
     double d[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-        d[c] = __dadd_rn(__dadd_rn(__dmul_rn(a.cam.cx[c], fx), __dmul_rn(a.cam.cy[c], fy)), a.cam.dir[c]);
+    d[0] = __dmul_rn(a.cam.cx[0], fx);
+    d[1] = __dadd_rn(__dmul_rn(a.cam.cy[1], fy), a.cam.dir[1]);
+    d[2] = __dadd_rn(__dmul_rn(a.cam.cy[2], fy), a.cam.dir[2]);
     const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2])));
     const double rn = __ddiv_rn(1.0, nrm);  // one true division, shared by the three components
 #pragma unroll
