@@ -210,6 +210,31 @@ def run_reference_arm(args, rank, emit):
     emit(line)
 
 
+def bind_to_gpu_numa(torch, local_rank):
+    """Pins this rank to the host cores of the NUMA node its GPU hangs off, BEFORE any pinned buffer is allocated (first touch puts
+    the pages there): with N ranks streaming 1.8 GB per step each through one host, crossing the socket interconnect is what costs."""
+    info = {"numa_node": None, "bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        info["host_numa_nodes"] = len(nodes)
+        if node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"] = True
+    except Exception as e:  # noqa: BLE001 -- containers often hide /sys: then nothing is bound and the line says so
+        info["error"] = str(e)[:80]
+    return info
+
+
 def strong_c3(pt, torch, dist, rank, world, local_rank, reps):
     """BASELINE config C3 -- the north-star frame -- rendered once by all ranks together; wall time per frame incl. the gather."""
     from ascendpathtracing_b200 import sharding
@@ -329,6 +354,7 @@ def main():
     if not torch.cuda.is_available() or pt.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(torch, local_rank) if world > 1 else {"numa_node": None, "bound": False}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -448,6 +474,7 @@ def main():
         e2e["link"] = {"copies_only_ms": l_ms, "aggregate_gbs": 36 * n * world / (l_ms * 1e-3) / 1e9, "e2e_aggregate_gbs": 36 * n * world / (e_ms * 1e-3) / 1e9,
                        "what": "all ranks at once: H2D of the rank's rays and D2H of its colours as two concurrent pinned copies, no kernel (best of 2)"}
         e2e["frac_of_link"] = l_ms / e_ms
+        e2e["host_numa"] = numa
         del h_rays, h_col
         # The whole run.sh-equivalent pipeline through one C-ABI call: scene (512 B, host) in, 8-bit stripe (host) out;
         # rays are generated on the device (counter-based RNG), traced and resolved tile by tile, nothing else crosses PCIe.
