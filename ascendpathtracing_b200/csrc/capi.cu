@@ -310,6 +310,56 @@ int ptb200::render_image_impl(const char *who, const PtParams *p, const PtMateri
     // ever fewer lanes busy: ~0.1 ms for the mirror kernel but 4-8 ms for the BVH material kernel (paths of up to 64
     // bounces; profiles/r1_c4_tail.md), so a frame should be as few launches as memory allows.  PTB200_TILE_PATHS overrides.
     static const int64_t target_paths = env_ll("PTB200_TILE_PATHS", 512LL << 20, 1024);
+    // Fused resolve (trace_kernels.cu, fuse_reduce_chunk), OPT-IN with PTB200_FUSED_RESOLVE=1: with S a power of two in 8..256
+    // and a constant-bank scene the trace kernel averages every sub-pixel run itself, in NumPy's order, and writes 12 bytes per
+    // RUN instead of 12 bytes per path; the frame is then one pass (launches of 2^30 paths) with 48 bytes of workspace per pixel
+    // instead of 6.4 GB.  Same image bit for bit (tests/test_gpu_fused_resolve.py).  It is not the default because it is not
+    // faster on B200: the kernel is bound by instruction issue, not by HBM, and the parked colours + in-kernel reduction cost
+    // more issue slots (C2: 2.71 ms against 2.56 ms) than the 0.10 ms the separate resolve kernel takes at 5.5 TB/s
+    // (profiles/r2_fused_resolve.md).  Read per call: the tests flip it.
+    const bool allow_fused = env_ll("PTB200_FUSED_RESOLVE", 0, 0) != 0;
+    if (allow_fused && tree == nullptr && fuse_supported(p->samples)) {
+        const int64_t npix = pix_end - pix_begin, m = npix * spp;
+        WsBlock wsm;
+        if ((rc = ws_alloc(sizeof(float) * 3 * 4 * static_cast<size_t>(npix), &wsm)) != PTB200_OK)
+            return rc;
+        FuseTarget fuse = {static_cast<float *>(wsm.ptr), 4 * npix};
+        cudaError_t e = cudaSuccess;
+        if (stats != nullptr)
+            e = cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), stream);
+        unsigned long long *seg_stat = stats ? reinterpret_cast<unsigned long long *>(stats) + 1 : nullptr;
+        // 32-bit generator indices: pieces of at most 2^30 paths (whole pixels), each its own generator range
+        const int64_t piece_pix = (1LL << 30) / spp;
+        for (int64_t q = pix_begin; q < pix_end && e == cudaSuccess; q += piece_pix) {
+            const int64_t np = (pix_end - q < piece_pix) ? pix_end - q : piece_pix;
+            const int64_t mm = np * spp;
+            const double *u = uniforms ? uniforms + 2 * (q - pix_begin) * spp : nullptr;
+            RayGenSource gen = make_raygen_source(*p, u, seed, q * spp, mm);
+            if (step > 1) {
+                if (!gen.fast_index) {
+                    e = cudaErrorInvalidValue;
+                    break;
+                }
+                gen.x_first = x_first, gen.x_step = step;
+            }
+            const FuseTarget piece = {fuse.means + (q - pix_begin) * 4, fuse.n_runs};
+            if (mp != nullptr)
+                e = trace_materials(stream, *p, *mp, nullptr, reinterpret_cast<const float *>(spheres), nullptr, mm, 0, mm,
+                                    static_cast<uint64_t>(q * spp), seg_stat, nullptr, &gen, &piece);
+            else
+                e = trace_paths(stream, *p, nullptr, reinterpret_cast<const float *>(spheres), nullptr, mm, 0, mm, seg_stat, &gen, &piece);
+        }
+        if (e == cudaSuccess)
+            e = resolve_means(stream, *p, fuse.means, fuse.n_runs, pix_begin, npix, image, x0, x1 - x0, gamma);
+        const unsigned long long total = static_cast<unsigned long long>(m);
+        if (e == cudaSuccess && stats != nullptr)
+            e = cudaMemcpyAsync(stats, &total, sizeof total, cudaMemcpyHostToDevice, stream);  // drained by the sync below
+        cudaError_t es = cudaStreamSynchronize(stream);
+        ws_free(&wsm);
+        if (e == cudaSuccess)
+            e = es;
+        return e == cudaSuccess ? PTB200_OK : fail_cuda(e, who);
+    }
     // Rays are generated inside the trace kernel (straight into its shared-memory ring) and never exist in HBM; only the
     // per-path colours of a tile (12 B/path) are materialised between the trace and the resolve kernel.  If the device
     // cannot spare the workspace (other tenants, a smaller GPU) the tile is halved until it fits, down to 16 Mi paths.

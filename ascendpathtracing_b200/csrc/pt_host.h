@@ -14,16 +14,25 @@ constexpr int kTraceThreads = 256;
 // the number of ray segments actually traced added to it.
 // gen (nullable): generate the rays inside the kernel instead of reading `rays` (which may then be NULL); element
 // `first` of the launch is the generator's element 0.
+// fuse (nullable; needs gen, no tree, fuse_supported(samples), whole runs): the kernel resolves on the fly -- instead of
+// per-path colours it writes the NumPy-order mean of every run of S consecutive paths: plane c of `means` ([3][n_runs]) at
+// (path - first) / S; `colors` is unused then.  resolve_means() finishes the image.
 struct RayGenSource;
+struct FuseTarget {
+    float *means;
+    int64_t n_runs;
+};
+bool fuse_supported(int samples);
 cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *rays, const float *spheres, float *colors, int64_t n,
-                        int64_t first, int64_t count, unsigned long long *stats, const RayGenSource *gen = nullptr);
+                        int64_t first, int64_t count, unsigned long long *stats, const RayGenSource *gen = nullptr,
+                        const FuseTarget *fuse = nullptr);
 
 // trace_kernels.cu -- material extension (pt_material.cuh): spheres is the 11-row SoA; element i of the slice has RNG
 // path index path0 + (i - first).
 // tree (nullable): a BVH built by ptb200_bvh_build over the same spheres; then `spheres` may be NULL.
 cudaError_t trace_materials(cudaStream_t stream, const PtParams &p, const PtMaterialParams &mp, const float *rays, const float *spheres,
                             float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats,
-                            const PtBvh *tree = nullptr, const RayGenSource *gen = nullptr);
+                            const PtBvh *tree = nullptr, const RayGenSource *gen = nullptr, const FuseTarget *fuse = nullptr);
 
 // bvh.cu
 struct BvhScene;
@@ -42,6 +51,11 @@ cudaError_t gen_rays(cudaStream_t stream, const PtParams &p, const double *unifo
 // [H][img_w][3] output whose column 0 is image column x_origin.
 cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *colors, int64_t cn, int64_t pix0, int64_t npix,
                            uint8_t *image, int32_t x_origin, int32_t img_w, int gamma = 0);
+
+// resolve_kernels.cu -- the second half of the fused resolve: run means [3][n_runs] (element 0 = sub-pixel run 0 of pixel
+// `pix0`, four runs per pixel) -> 8-bit pixels, same image conventions as resolve_pixels.
+cudaError_t resolve_means(cudaStream_t stream, const PtParams &p, const float *means, int64_t n_runs, int64_t pix0, int64_t npix,
+                          uint8_t *image, int32_t x_origin, int32_t img_w, int gamma = 0);
 
 // fp32_peak.cu
 cudaError_t measure_fp32(int kind, int iters, double *gops, double *ms);

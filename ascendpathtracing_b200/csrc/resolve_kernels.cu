@@ -322,7 +322,86 @@ __global__ void __launch_bounds__(256) resolve_tiles_kernel(const float *__restr
     }
 }
 
+// ---- second half of the fused resolve: run means -> pixels -------------------------------------------------------------
+// The trace kernels of the production entries already averaged every sub-pixel run (trace_kernels.cu, fuse_reduce_chunk);
+// what is left per pixel and channel is data_visualization.py:39-57: the four means summed in binary64, / 4, clip, x 255,
+// truncate.  One thread per pixel (its four means are one 128-bit load per plane; consecutive threads walk down a column, so
+// loads coalesce), results staged per 16 x 16 tile and written as 128-bit row segments like resolve_tiles_kernel.
+__device__ __forceinline__ uint8_t finish_channel(float4 m, int gamma) {
+    double v = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(static_cast<double>(m.x), static_cast<double>(m.y)), static_cast<double>(m.z)),
+                                   static_cast<double>(m.w)),
+                         4.0);
+    v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    if (gamma)  // smallpt's display transform (material extension only; the reference has no gamma)
+        v = pow(v, 1.0 / 2.2) * 255.0 + 0.5;
+    else
+        v = __dmul_rn(v, 255.0);
+    return static_cast<uint8_t>(static_cast<int>(v));
+}
+
+__global__ void __launch_bounds__(256) resolve_means_kernel(const float *__restrict__ means, int64_t n_runs, int64_t pix0, int64_t npix, int h,
+                                                            uint8_t *__restrict__ image, int x_origin, int img_w, int gamma, int vector_rows) {
+    __shared__ __align__(16) uint8_t tile[kTileRows][kTileCols * 3];
+    const int xa = static_cast<int>(pix0 / h), xb = static_cast<int>((pix0 + npix - 1) / h);
+    const int tiles_y = (h + kTileRows - 1) / kTileRows;
+    const int64_t n_tiles = static_cast<int64_t>((xb - xa) / kTileCols + 1) * tiles_y;
+    const int col = threadIdx.x >> 4, rp = threadIdx.x & 15;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tx = static_cast<int>(t / tiles_y), ty = static_cast<int>(t - static_cast<int64_t>(tx) * tiles_y);
+        const int x_tile = xa + tx * kTileCols, y_tile = ty * kTileRows;
+        {
+            const int x = x_tile + col, y = y_tile + rp;
+            const int64_t q = static_cast<int64_t>(x) * h + y - pix0;
+            if (x <= xb && y < h && q >= 0 && q < npix) {
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    tile[kTileRows - 1 - rp][col * 3 + c] = finish_channel(__ldg(reinterpret_cast<const float4 *>(means + c * n_runs) + q), gamma);
+            }
+        }
+        __syncthreads();
+        const int64_t first_q = static_cast<int64_t>(x_tile) * h + y_tile - pix0;
+        const int64_t last_q = static_cast<int64_t>(x_tile + kTileCols - 1) * h + y_tile + kTileRows - 1 - pix0;
+        const bool whole = vector_rows && x_tile + kTileCols - 1 <= xb && y_tile + kTileRows <= h && first_q >= 0 && last_q < npix;
+        if (whole) {
+            if (threadIdx.x < kTileRows * 3) {
+                const int r = threadIdx.x / 3, part = threadIdx.x - r * 3;
+                const int y = y_tile + kTileRows - 1 - r;
+                uint8_t *dst = image + (static_cast<int64_t>(h - 1 - y) * img_w + (x_tile - x_origin)) * 3 + part * 16;
+                *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(&tile[r][part * 16]);
+            }
+        } else {  // ragged tile (frame edge, range edge, unaligned rows): byte stores of the valid pixels
+            const int r = threadIdx.x >> 4, c2 = threadIdx.x & 15;
+            const int x = x_tile + c2, y = y_tile + kTileRows - 1 - r;
+            const int64_t q = static_cast<int64_t>(x) * h + y - pix0;
+            if (x <= xb && y < h && q >= 0 && q < npix) {
+                uint8_t *dst = image + (static_cast<int64_t>(h - 1 - y) * img_w + (x - x_origin)) * 3;
+                dst[0] = tile[r][c2 * 3], dst[1] = tile[r][c2 * 3 + 1], dst[2] = tile[r][c2 * 3 + 2];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
+
+cudaError_t resolve_means(cudaStream_t stream, const PtParams &p, const float *means, int64_t n_runs, int64_t pix0, int64_t npix, uint8_t *image,
+                          int32_t x_origin, int32_t img_w, int gamma) {
+    if (npix <= 0)
+        return cudaSuccess;
+    if (reinterpret_cast<uintptr_t>(means) % 16 != 0 || n_runs % 4 != 0)  // one 128-bit load per pixel and plane
+        return cudaErrorInvalidValue;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int xa = static_cast<int>(pix0 / p.height), xb = static_cast<int>((pix0 + npix - 1) / p.height);
+    const int64_t n_tiles = static_cast<int64_t>((xb - xa) / kTileCols + 1) * ((p.height + kTileRows - 1) / kTileRows);
+    const int vector_rows = reinterpret_cast<uintptr_t>(image) % 16 == 0 && (static_cast<int64_t>(img_w) * 3) % 16 == 0 &&
+                            (static_cast<int64_t>(xa - x_origin) * 3) % 16 == 0;
+    const int64_t cap_tiles = static_cast<int64_t>(sms) * 8;
+    resolve_means_kernel<<<static_cast<unsigned>(n_tiles < cap_tiles ? n_tiles : cap_tiles), 256, 0, stream>>>(means, n_runs, pix0, npix, p.height,
+                                                                                                             image, x_origin, img_w, gamma, vector_rows);
+    return cudaGetLastError();
+}
 
 cudaError_t resolve_pixels(cudaStream_t stream, const PtParams &p, const float *colors, int64_t cn, int64_t pix0, int64_t npix,
                            uint8_t *image, int32_t x_origin, int32_t img_w, int gamma) {

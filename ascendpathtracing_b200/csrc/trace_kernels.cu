@@ -89,28 +89,147 @@ static __device__ __noinline__ void generate_ray_to_ring(unsigned int path, floa
         slot[c * kRing] = r[c];
 }
 
-template <bool GEN> struct PathFeeder {
+// ---- fused resolve (FUSE): the production entries never materialise per-path colours ------------------------------------
+// NumPy averages the S samples of a sub-pixel run in a fixed order (resolve_kernels.cu), and paths finish out of order here,
+// so a finished path parks its colour in a small per-warp scratch -- [3 planes][2 chunk slots][kChunkPaths] floats of global
+// memory that the warp keeps rewriting, i.e. that lives in L2 and costs no shared memory -- and when every path of a chunk
+// has retired the warp itself reduces the chunk's runs in NumPy's order (128-bit L2 loads, two lanes per run block as in
+// resolve_tiles_kernel) and stores ONE float per run and channel: the run's mean.  12 bytes per S paths leave the SM instead of
+// 12 bytes per path, and the frame needs no colour workspace (C3: 0.4 GB of run means instead of 102 GB of colours written
+// and read back).  Needs chunks made of whole runs whose NumPy recursion stays inside one chunk: S a power of two, 8..256.
+constexpr int kChunkPaths = 32 * kChunkBatches;
+constexpr int kFuseScratchFloats = 3 * 2 * kChunkPaths;  // per warp: [3 planes][2 chunk slots][kChunkPaths]
+static_assert(kChunkPaths == 256, "the fused resolve assumes 256-path chunks (S up to 256 = NumPy's 128 + 128 split)");
+
+struct FuseOut {
+    float *mean[3];   // run means of this launch: plane c, element = (path of the launch) / S
+    float *scratch;   // kFuseScratchFloats floats per warp of the grid
+    unsigned int log2_s;
+    float inv_s;      // 1 / S, a power of two: fl(sum * inv_s) == fl(sum / S), NumPy's float32 division
+};
+static __constant__ FuseOut c_fuse;
+
+__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+
+// Reduces the `valid` (a multiple of S) retired paths of one chunk slot: for every run and channel NumPy's pairwise sum
+// (scripts/data_visualization.py:39-45 -> np.mean over a contiguous float32 axis) and the float32 division by S.
+// Two lanes own one block of min(S, 128) samples: lane `half` holds accumulators r[4 half .. 4 half + 3] of NumPy's eight,
+// fed in sample order by 128-bit loads; ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) is two in-lane adds and one shuffle; S = 256
+// adds its two block sums (neighbouring lane pairs).  LG = log2(S) at compile time: the block loop unrolls completely.
+template <int LG> __device__ __forceinline__ void fuse_reduce_chunk_s(const float *slot, float *const (&mean)[3], unsigned int first,
+                                                                      unsigned int valid, unsigned int lane, float inv_s) {
+    constexpr unsigned int kLgBlk = LG > 7 ? 7 : LG;  // NumPy's unrolled block: up to 128 samples
+    constexpr unsigned int kBlk = 1u << kLgBlk;
+    constexpr bool kTwoBlocks = LG > 7;               // S = 256: two blocks per run
+    const unsigned int per_plane = valid >> kLgBlk;   // block tasks per colour plane
+    const unsigned int total = 3u * per_plane;
+    const unsigned int half = lane & 1u;
+    const unsigned int run0 = first >> LG;
+    for (unsigned int t0 = 0; t0 < total; t0 += 16u) {  // warp-uniform
+        const unsigned int t = t0 + (lane >> 1);
+        const bool live = t < total;
+        const unsigned int tt = live ? t : 0u;           // idle pairs redo task 0 (they take part in the shuffles)
+        const unsigned int ch = (tt >= per_plane ? 1u : 0u) + (tt >= 2u * per_plane ? 1u : 0u);
+        const unsigned int rest = tt - ch * per_plane;   // block index inside the plane
+        const float *a = slot + (ch * (2 * kChunkPaths) + (rest << kLgBlk) + 4u * half);
+        constexpr unsigned int kLoads = kBlk / 8, kInFlight = kLoads < 4 ? kLoads : 4;  // L2 latency is paid kLoads / 4 times
+        float4 acc = ldcg4(a);
+#pragma unroll
+        for (unsigned int g = 0; g < kLoads; g += kInFlight) {
+            float4 v[kInFlight];
+#pragma unroll
+            for (unsigned int i = (g == 0 ? 1 : 0); i < kInFlight; i++)
+                v[i] = ldcg4(a + 8u * (g + i));
+#pragma unroll
+            for (unsigned int i = (g == 0 ? 1 : 0); i < kInFlight; i++)
+                acc.x = __fadd_rn(acc.x, v[i].x), acc.y = __fadd_rn(acc.y, v[i].y), acc.z = __fadd_rn(acc.z, v[i].z), acc.w = __fadd_rn(acc.w, v[i].w);
+        }
+        const float q = __fadd_rn(__fadd_rn(acc.x, acc.y), __fadd_rn(acc.z, acc.w));
+        float r = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 1));  // float addition commutes: both lanes hold the block sum
+        if (kTwoBlocks)
+            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));    // the run's other block (neighbouring lane pair)
+        const unsigned int run = kTwoBlocks ? rest >> 1 : rest;
+        if (live && half == 0u && (!kTwoBlocks || (rest & 1u) == 0u))
+            mean[ch][run0 + run] = __fmul_rn(r, inv_s);
+    }
+}
+
+// Out of line: runs once per 256 paths and borrows its registers for a moment (like the ray generator).
+static __device__ __noinline__ void fuse_reduce_chunk(const float *slot, unsigned int first, unsigned int valid, unsigned int lane) {
+    float *const mean[3] = {c_fuse.mean[0], c_fuse.mean[1], c_fuse.mean[2]};
+    const float inv_s = c_fuse.inv_s;
+    switch (c_fuse.log2_s) {  // warp-uniform
+    case 3: fuse_reduce_chunk_s<3>(slot, mean, first, valid, lane, inv_s); break;
+    case 4: fuse_reduce_chunk_s<4>(slot, mean, first, valid, lane, inv_s); break;
+    case 5: fuse_reduce_chunk_s<5>(slot, mean, first, valid, lane, inv_s); break;
+    case 6: fuse_reduce_chunk_s<6>(slot, mean, first, valid, lane, inv_s); break;
+    case 7: fuse_reduce_chunk_s<7>(slot, mean, first, valid, lane, inv_s); break;
+    default: fuse_reduce_chunk_s<8>(slot, mean, first, valid, lane, inv_s); break;
+    }
+}
+
+template <bool GEN, bool FUSE = false> struct PathFeeder {
     const TracePlanes &pl;
     float *ring;
     unsigned long long *counter;
     unsigned int count, lane;
     unsigned int chunk_even, chunk_odd;  // first path of the chunk with even / odd sequence number (>= count: no such chunk)
     unsigned int issued, head;
+    unsigned int scratch;                // FUSE: index of this warp's colour scratch in c_fuse.scratch
+    bool postponed;                      // FUSE: a chunk claim is waiting for a straggler (warp-uniform)
 
     // GEN: rays are generated straight into the ring (c_gen) and never exist in HBM; pl.ray is unused then.
     __device__ __forceinline__ PathFeeder(const TracePlanes &planes, float *ring_, unsigned long long *counter_, unsigned int count_,
                                           unsigned int lane_)
-        : pl(planes), ring(ring_), counter(counter_), count(count_), lane(lane_), issued(0), head(0) {
+        : pl(planes), ring(ring_), counter(counter_), count(count_), lane(lane_), issued(0), head(0), scratch(0), postponed(false) {
         chunk_even = chunk_odd = count_;
+        if (FUSE)
+            scratch = (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * kFuseScratchFloats;
         for (int b = 0; b < kRingBatches; b++)
-            issue();
+            issue(false, 0u);
+    }
+    // FUSE: where the colour of the path with warp-local sequence number seq is parked (plane c at [c * 2 * kChunkPaths]):
+    // one IMAD.WIDE off the constant-bank base, the three stores share the address register
+    __device__ __forceinline__ float *park(unsigned int seq) const { return c_fuse.scratch + (scratch + (seq % (2 * kChunkPaths))); }
+    __device__ __forceinline__ void reduce_slot(unsigned int parity) {
+        const unsigned int first = parity ? chunk_odd : chunk_even;
+        if (first < count) {  // warp-uniform
+            __syncwarp();     // the lanes' parked colours are visible to the whole warp
+            fuse_reduce_chunk(c_fuse.scratch + (scratch + parity * kChunkPaths), first, count - first < kChunkPaths ? count - first : kChunkPaths, lane);
+        }
+    }
+    // FUSE, after the last path has retired: the (at most two) chunks not yet reduced, oldest first
+    __device__ __forceinline__ void finish() {
+        const unsigned int chunks = (issued + kChunkBatches - 1) / kChunkBatches;
+        if (chunks >= 2u)
+            reduce_slot((chunks - 2u) & 1u);
+        if (chunks >= 1u)
+            reduce_slot((chunks - 1u) & 1u);
     }
     __device__ __forceinline__ unsigned int path_of(unsigned int seq) const {  // warp-local sequence number -> path index
         const unsigned int batch = seq >> 5;
         return (((batch / kChunkBatches) & 1u) ? chunk_odd : chunk_even) + (batch % kChunkBatches) * 32u + (seq & 31u);
     }
-    __device__ __forceinline__ void issue() {  // warp-uniform: every lane commits a (possibly empty) group
+    // warp-uniform: every lane commits a (possibly empty) group.  holds / held_seq: this lane holds an unfinished path and its
+    // sequence number (FUSE only).  Returns true when a claim that had been postponed has just gone through: lanes that went
+    // idle in the meantime ask for a path again.
+    __device__ __forceinline__ bool issue(bool holds, unsigned int held_seq) {
+        bool rearm = false;
         if (issued % kChunkBatches == 0) {
+            if (FUSE && issued >= 2u * kChunkBatches) {
+                // The new chunk takes over the scratch slot of the chunk two back, which is reduced first -- once its last path
+                // has retired.  A straggler (a path of that chunk still bouncing: only with paths far longer than average)
+                // postpones the claim: take() hands out nothing beyond what was issued, lanes that find the ring dry go idle, and
+                // the warp tries again at its next swap (there is one: the straggler's own).  In practice the ring's four
+                // batches outlast any path (depth 50: ~55 iterations of supply).
+                if (__any_sync(0xffffffffu, holds && held_seq < (issued - kChunkBatches) * 32u)) {
+                    postponed = true;
+                    return false;
+                }
+                rearm = postponed;
+                postponed = false;
+                reduce_slot((issued / kChunkBatches) & 1u);
+            }
             unsigned long long base = 0;
             if (lane == 0)
                 base = atomicAdd(counter, static_cast<unsigned long long>(32 * kChunkBatches));
@@ -136,33 +255,39 @@ template <bool GEN> struct PathFeeder {
         if (!GEN)
             __pipeline_commit();
         issued++;
+        return rearm;
     }
     // Called by the whole warp when at least one lane wants a path.  Lanes that get one receive its index and a pointer
     // to its ray in the ring (component c at slot[c * kRing]); the caller reads it and then calls refill().
-    __device__ __forceinline__ bool take(bool want, unsigned int wmask, unsigned int &path, const float *&slot) {
+    // seq: the path's warp-local sequence number (FUSE parks its colour by it).  FUSE never hands out a sequence number that has
+    // not been issued (the ring can run dry behind a postponed chunk claim).
+    __device__ __forceinline__ bool take(bool want, unsigned int wmask, unsigned int &path, unsigned int &seq, const float *&slot) {
         unsigned int lt;
         asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-        const unsigned int seq = head + __popc(wmask & lt);
+        seq = head + __popc(wmask & lt);
         path = path_of(seq);
-        const bool got = want && path < count;
+        const bool got = want && path < count && (!FUSE || seq < issued * 32u);
         if (!GEN)
             __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
         __syncwarp();                  // ... and is visible to the other lanes of the warp
         slot = ring + (seq & (kRing - 1));
         head += __popc(wmask);
+        if (FUSE)
+            head = min(head, issued * 32u);
         return got;
     }
-    __device__ __forceinline__ void refill() {
+    __device__ __forceinline__ bool refill(bool holds = false, unsigned int held_seq = 0u) {
         __syncwarp();  // ring reads done before a slot can be refilled
         if (issued < head / 32u + kRingBatches)
-            issue();
+            return issue(holds, held_seq);
+        return false;
     }
 };
 
 #ifndef PTB_BLOCKS_PER_SM
 #define PTB_BLOCKS_PER_SM 5
 #endif
-template <int NS, bool EARLY, bool GEN>
+template <int NS, bool EARLY, bool GEN, bool FUSE = false>
 __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                        int depth, int nsph, int stride, int light, float scale, float one,
                                                                        unsigned long long *__restrict__ stats, unsigned long long *work_counter) {
@@ -177,7 +302,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
     // flight) the colours they store share cache lines.  See PathFeeder for how paths reach the warp.
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    PathFeeder<GEN> feed(pl, reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
+    PathFeeder<GEN, FUSE> feed(pl, reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
 
     PathState p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -186,7 +311,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
     p.alive = true;
     int bounce = 0;
     unsigned int segs = 0;
-    unsigned int mine = 0;      // path this lane holds
+    unsigned int mine = 0;      // path this lane holds (FUSE: its warp-local sequence number)
     bool active = false;        // this lane holds a real path
     bool want = true;           // this lane needs a (new) path
 
@@ -194,26 +319,37 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
         const unsigned int wmask = __ballot_sync(0xffffffffu, want);
         if (wmask != 0u) {  // warp-uniform
             if (active && want) {  // lanes that finished a path in the previous iteration
-                pl.col[0][mine] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
-                pl.col[1][mine] = __fmul_rn(p.rg, scale);
-                pl.col[2][mine] = __fmul_rn(p.rb, scale);
+                if (FUSE) {        // parked for the warp's own resolve (fuse_reduce_chunk)
+                    float *park = feed.park(mine);
+                    park[0 * kChunkPaths] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
+                    park[2 * kChunkPaths] = __fmul_rn(p.rg, scale);
+                    park[4 * kChunkPaths] = __fmul_rn(p.rb, scale);
+                } else {
+                    pl.col[0][mine] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
+                    pl.col[1][mine] = __fmul_rn(p.rg, scale);
+                    pl.col[2][mine] = __fmul_rn(p.rb, scale);
+                }
                 segs += bounce;
             }
-            unsigned int path;
+            unsigned int path, seq;
             const float *slot;
-            const bool got = feed.take(want, wmask, path, slot);
+            const bool got = feed.take(want, wmask, path, seq, slot);
             if (got) {
                 p.ox = slot[0 * kRing], p.oy = slot[1 * kRing], p.oz = slot[2 * kRing];
                 p.dx = slot[3 * kRing], p.dy = slot[4 * kRing], p.dz = slot[5 * kRing];
-                mine = path;
+                mine = FUSE ? seq : path;
             }
-            feed.refill();
+            const bool rearm = feed.refill(want ? got : active, mine);  // warp-uniform; FUSE only, and next to never
             if (want) {
                 active = got;
                 p.rr = p.rg = p.rb = 1.0f;
                 p.alive = true;
                 bounce = 0;
                 want = false;
+            }
+            if (FUSE && rearm) {
+                want = !active;
+                continue;
             }
             if (!__any_sync(0xffffffffu, active))
                 break;
@@ -225,6 +361,8 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
         bounce++;
         want = active && ((bounce >= depth) || (EARLY && path_settled(p, zero_stop)));
     }
+    if (FUSE)
+        feed.finish();
     if (stats != nullptr) {
         unsigned int w = segs;
 #pragma unroll
@@ -238,7 +376,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
 
 // ---- material extension kernel (pt_material.cuh), constant-bank scenes -----------------------------------------------
 // Same persistent warps, ring and ballot-ranked regeneration; one iteration = one bounce of material_bounce().
-template <int NS, bool GEN>
+template <int NS, bool GEN, bool FUSE = false>
 __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const TracePlanes pl, const float *__restrict__ spheres, unsigned int count,
                                                                            int max_depth, int rr_start, int nsph, int stride, float eps, float one,
                                                                            unsigned long long seed, unsigned long long path0,
@@ -248,7 +386,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
     stage_materials_shared(smem, spheres, nsph, stride, sh);
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    PathFeeder<GEN> feed(pl, reinterpret_cast<float *>(smem + 3 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
+    PathFeeder<GEN, FUSE> feed(pl, reinterpret_cast<float *>(smem + 3 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
 
     MatPath p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -256,32 +394,42 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
     p.tr = p.tg = p.tb = 1.0f;
     p.lr = p.lg = p.lb = 0.0f;
     p.depth = 0;
-    unsigned int segs = 0, mine = 0;
+    unsigned int segs = 0, mine = 0, mine_seq = 0;
     bool active = false, want = true;
 
     for (;;) {
         const unsigned int wmask = __ballot_sync(0xffffffffu, want);
         if (wmask != 0u) {
             if (active && want) {
-                pl.col[0][mine] = p.lr;
-                pl.col[1][mine] = p.lg;
-                pl.col[2][mine] = p.lb;
+                if (FUSE) {  // parked for the warp's own resolve (fuse_reduce_chunk)
+                    float *park = feed.park(mine_seq);
+                    park[0 * kChunkPaths] = p.lr, park[2 * kChunkPaths] = p.lg, park[4 * kChunkPaths] = p.lb;
+                } else {
+                    pl.col[0][mine] = p.lr;
+                    pl.col[1][mine] = p.lg;
+                    pl.col[2][mine] = p.lb;
+                }
             }
-            unsigned int path;
+            unsigned int path, seq;
             const float *slot;
-            const bool got = feed.take(want, wmask, path, slot);
+            const bool got = feed.take(want, wmask, path, seq, slot);
             if (got) {
                 p.ox = slot[0 * kRing], p.oy = slot[1 * kRing], p.oz = slot[2 * kRing];
                 p.dx = slot[3 * kRing], p.dy = slot[4 * kRing], p.dz = slot[5 * kRing];
                 mine = path;
+                mine_seq = seq;
             }
-            feed.refill();
+            const bool rearm = feed.refill(want ? got : active, mine_seq);  // warp-uniform; FUSE only, and next to never
             if (want) {
                 active = got;
                 p.tr = p.tg = p.tb = 1.0f;
                 p.lr = p.lg = p.lb = 0.0f;
                 p.depth = 0;
                 want = false;
+            }
+            if (FUSE && rearm) {
+                want = !active;
+                continue;
             }
             if (!__any_sync(0xffffffffu, active))
                 break;
@@ -294,6 +442,8 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
             want = ended || p.depth >= max_depth;
         }
     }
+    if (FUSE)
+        feed.finish();
     if (stats != nullptr) {
         unsigned int w = segs;
 #pragma unroll
@@ -621,10 +771,12 @@ struct DeviceState {
     bool init = false;
     int device = 0;
     int sm_count = 0;
-    int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [GEN?][NS8?][EARLY?]
+    int blocks_per_sm[16] = {};  // [FUSE?][GEN?][NS8?][EARLY?]
     SceneConst *scene_alias = nullptr;
     int *zero_ok_alias = nullptr;
     unsigned long long *work_counter = nullptr;  // chunk dispenser of the persistent kernels (reset before every launch)
+    float *fuse_scratch = nullptr;     // fused resolve: kFuseScratchFloats per warp of the largest grid launched so far
+    size_t fuse_scratch_warps = 0;
     cudaEvent_t scene_free = nullptr;  // recorded after the last kernel that reads the staged scene
     cudaStream_t last_stream = nullptr;
     bool have_last = false;
@@ -634,8 +786,33 @@ constexpr int kMaxDevices = 64;
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mu;
 
-template <int NS, bool EARLY, bool GEN> cudaError_t occupancy(int *out, size_t smem) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, trace_paths_kernel<NS, EARLY, GEN>, kTraceThreads, smem);
+template <int NS, bool EARLY, bool GEN, bool FUSE> cudaError_t occupancy(int *out, size_t smem) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, trace_paths_kernel<NS, EARLY, GEN, FUSE>, kTraceThreads, smem);
+}
+
+// Fused resolve: points c_fuse at the run means of the launch that starts at path `a` of the call's range and makes sure the
+// per-warp colour scratch covers `grid` blocks.  Caller holds g_mu and has ordered the stream behind earlier launches.
+cudaError_t stage_fuse(DeviceState &s, cudaStream_t stream, const FuseTarget &f, int64_t a, int samples, int grid) {
+    const size_t warps = static_cast<size_t>(grid) * kWarpsPerBlock;
+    if (warps > s.fuse_scratch_warps) {
+        cudaError_t e = cudaSuccess;
+        if (s.fuse_scratch != nullptr && (e = cudaFree(s.fuse_scratch)) != cudaSuccess)  // waits for the kernels that use it
+            return e;
+        s.fuse_scratch = nullptr, s.fuse_scratch_warps = 0;
+        if ((e = cudaMalloc(reinterpret_cast<void **>(&s.fuse_scratch), warps * kFuseScratchFloats * sizeof(float))) != cudaSuccess)
+            return e;
+        s.fuse_scratch_warps = warps;
+    }
+    unsigned int lg = 0;
+    while ((1 << lg) < samples)
+        lg++;
+    FuseOut o;
+    for (int c = 0; c < 3; c++)
+        o.mean[c] = f.means + c * f.n_runs + a / samples;
+    o.scratch = s.fuse_scratch;
+    o.log2_s = lg;
+    o.inv_s = 1.0f / static_cast<float>(samples);
+    return cudaMemcpyToSymbolAsync(c_fuse, &o, sizeof o, 0, cudaMemcpyHostToDevice, stream);
 }
 
 // Stages the ray generator's parameters (fused generate-and-trace launches); caller holds g_mu and has ordered the stream.
@@ -682,17 +859,18 @@ cudaError_t check_stream_device(const DeviceState &s, cudaStream_t stream) {
     return sd == s.device ? cudaSuccess : cudaErrorInvalidDevice;
 }
 
-template <int NS, bool EARLY, bool GEN>
+template <int NS, bool EARLY, bool GEN, bool FUSE = false>
 cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays, const float *spheres, float *colors, int64_t n,
-                         int64_t first, int64_t count, const PtParams &p, unsigned long long *stats, const RayGenSource *gen) {
+                         int64_t first, int64_t count, const PtParams &p, unsigned long long *stats, const RayGenSource *gen,
+                         const FuseTarget *fuse = nullptr) {
     const size_t smem = sizeof(float4) * 2 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
-    int &occ = s.blocks_per_sm[(GEN ? 4 : 0) + (NS > 0 ? 2 : 0) + (EARLY ? 1 : 0)];
+    int &occ = s.blocks_per_sm[(FUSE ? 8 : 0) + (GEN ? 4 : 0) + (NS > 0 ? 2 : 0) + (EARLY ? 1 : 0)];
     if (occ == 0 || NS == 0) {
         cudaError_t e = cudaSuccess;
         if (smem > 48 * 1024 &&  // 769..1024 spheres: opt in to more than the default 48 KB of dynamic shared memory
-            (e = cudaFuncSetAttribute(trace_paths_kernel<NS, EARLY, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+            (e = cudaFuncSetAttribute(trace_paths_kernel<NS, EARLY, GEN, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
             return e;
-        if ((e = occupancy<NS, EARLY, GEN>(&occ, smem)) != cudaSuccess)
+        if ((e = occupancy<NS, EARLY, GEN, FUSE>(&occ, smem)) != cudaSuccess)
             return e;
         if (occ < 1) {  // the kernel cannot be resident at all with this much shared memory: fail loudly, do not guess a grid
             occ = 0;
@@ -707,7 +885,7 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
         for (int c = 0; c < 6; c++)
             pl.ray[c] = GEN ? nullptr : rays + c * n + a;
         for (int c = 0; c < 3; c++)
-            pl.col[c] = colors + c * n + a;
+            pl.col[c] = FUSE ? nullptr : colors + c * n + a;
         const int64_t need = (m + kTraceThreads - 1) / kTraceThreads;
         const int grid = static_cast<int>(need < cap ? need : cap);
         cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned long long), stream);
@@ -720,7 +898,9 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
             if ((e = stage_gen(stream, g)) != cudaSuccess)
                 return e;
         }
-        trace_paths_kernel<NS, EARLY, GEN><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), p.depth,
+        if (FUSE && (e = stage_fuse(s, stream, *fuse, a - first, p.samples, grid)) != cudaSuccess)
+            return e;
+        trace_paths_kernel<NS, EARLY, GEN, FUSE><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, static_cast<unsigned int>(m), p.depth,
                                                                                   p.sphere_count, p.sphere_stride, p.light_index, p.emission_scale,
                                                                                   1.0f, stats, s.work_counter);
         e = cudaGetLastError();
@@ -732,10 +912,14 @@ cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays,
 
 }  // namespace
 
+bool fuse_supported(int samples) { return samples >= 8 && samples <= kChunkPaths && (samples & (samples - 1)) == 0; }
+
 cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *rays, const float *spheres, float *colors, int64_t n,
-                        int64_t first, int64_t count, unsigned long long *stats, const RayGenSource *gen) {
+                        int64_t first, int64_t count, unsigned long long *stats, const RayGenSource *gen, const FuseTarget *fuse) {
     if (count <= 0)
         return cudaSuccess;
+    if (fuse != nullptr && (gen == nullptr || !fuse_supported(p.samples) || first % p.samples != 0 || count % p.samples != 0))
+        return cudaErrorInvalidValue;
     std::lock_guard<std::mutex> lock(g_mu);
     DeviceState *s = nullptr;
     cudaError_t e = ensure_device_state(&s);
@@ -761,7 +945,12 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
         return v >= 1 ? v : 5;
     }();
     const bool early = !(p.flags & PTB200_F_FIXED_DEPTH) && p.depth >= min_early_depth;
-    if (p.sphere_count == 8)
+    if (fuse != nullptr)
+        e = p.sphere_count == 8 ? (early ? launch_trace<8, true, true, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen, fuse)
+                                         : launch_trace<8, false, true, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen, fuse))
+                                : (early ? launch_trace<0, true, true, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen, fuse)
+                                         : launch_trace<0, false, true, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen, fuse));
+    else if (p.sphere_count == 8)
         e = early ? (gen ? launch_trace<8, true, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen)
                          : launch_trace<8, true, false>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen))
                   : (gen ? launch_trace<8, false, true>(*s, stream, rays, spheres, colors, n, first, count, p, stats, gen)
@@ -783,9 +972,11 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
 
 cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtMaterialParams &mp, const float *rays, const float *spheres_in,
                             float *colors, int64_t n, int64_t first, int64_t count, uint64_t path0, unsigned long long *stats, const PtBvh *tree,
-                            const RayGenSource *gen) {
+                            const RayGenSource *gen, const FuseTarget *fuse) {
     if (count <= 0)
         return cudaSuccess;
+    if (fuse != nullptr && (gen == nullptr || tree != nullptr || !fuse_supported(p_in.samples) || first % p_in.samples != 0 || count % p_in.samples != 0))
+        return cudaErrorInvalidValue;
     // With a tree, the constant bank and the kernel's brute-force loop see only the huge spheres (compacted SoA, stride 1024).
     PtParams p = p_in;
     const float *spheres = spheres_in;
@@ -840,7 +1031,7 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
         for (int c = 0; c < 6; c++)
             pl.ray[c] = rays + c * n + a;
         for (int c = 0; c < 3; c++)
-            pl.col[c] = colors + c * n + a;
+            pl.col[c] = fuse ? nullptr : colors + c * n + a;
         // the wavefront kernel keeps kPool paths per warp in flight, the lock-step kernels one per lane
         const int64_t per_block = use_tree ? static_cast<int64_t>(kPool) * kWarpsPerBlock : kTraceThreads;
         const int64_t need = (m + per_block - 1) / per_block;
@@ -854,8 +1045,11 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
             if ((e = stage_gen(stream, make_raygen_source_shifted(*gen, a - first, m))) != cudaSuccess)
                 return e;
         }
-#define PTB_LAUNCH_MAT(NSV, GENV)                                                                                                            \
-    trace_materials_kernel<NSV, GENV><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start, p.sphere_count,          \
+        if (fuse != nullptr && (e = stage_fuse(*s, stream, *fuse, a - first, p.samples, grid)) != cudaSuccess)
+            return e;
+#define PTB_LAUNCH_MAT(NSV, GENV, ...)                                                                                                       \
+    trace_materials_kernel<NSV, GENV, ##__VA_ARGS__><<<grid, kTraceThreads, smem, stream>>>(pl, spheres, mm, mp.max_depth, mp.rr_start,          \
+                                                                             p.sphere_count,                                                  \
                                                                              p.sphere_stride, mp.hit_epsilon, 1.0f, mp.seed, pp, stats,        \
                                                                              s->work_counter)
         if (use_tree) {
@@ -873,9 +1067,9 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
                                                                                        mp.hit_epsilon, 1.0f, mp.seed, pp, stats, bvh, s->work_counter,
                                                                                        static_cast<unsigned int>(chunk));
         } else if (ten) {
-            if (gen) PTB_LAUNCH_MAT(10, true); else PTB_LAUNCH_MAT(10, false);
+            if (fuse) PTB_LAUNCH_MAT(10, true, true); else if (gen) PTB_LAUNCH_MAT(10, true); else PTB_LAUNCH_MAT(10, false);
         } else {
-            if (gen) PTB_LAUNCH_MAT(0, true); else PTB_LAUNCH_MAT(0, false);
+            if (fuse) PTB_LAUNCH_MAT(0, true, true); else if (gen) PTB_LAUNCH_MAT(0, true); else PTB_LAUNCH_MAT(0, false);
         }
 #undef PTB_LAUNCH_MAT
         if ((e = cudaGetLastError()) != cudaSuccess)
