@@ -145,6 +145,7 @@ __device__ __forceinline__ void ldg_node(const QNode *n, uint4 &L, uint4 &R) {
 // never replace the current best, so the square root is skipped for it.
 __device__ __forceinline__ void bvh_leaf(const BvhScene &sc, int sphere, float ox, float oy, float oz, float dx, float dy, float dz, float eps,
                                          float &tmin, int &idx) {
+    PTB_CHECK(sphere >= 0 && sphere < sc.n_big + sc.n_small);
     const float4 g = __ldg(sc.geom + sphere);
     const float ocx = __fsub_rn(g.x, ox);
     const float ocy = __fsub_rn(g.y, oy);
@@ -172,8 +173,10 @@ __device__ __forceinline__ void bvh_leaf(const BvhScene &sc, int sphere, float o
 template <class Stack>
 __device__ __forceinline__ void bvh_step_boxes(const BvhScene &sc, const BvhRay &r, float tmin, int &node, int &leaf_a, int &leaf_b, Stack &st) {
     uint4 L, R;
+    PTB_CHECK(node >= 0 && node < sc.n_small - 1);
     ldg_node(sc.qnodes + node, L, R);
     const int left = static_cast<int>(L.w), right = static_cast<int>(R.w);
+    PTB_CHECK((left >= 0 ? left : ~left) < sc.n_big + sc.n_small && (right >= 0 ? right : ~right) < sc.n_big + sc.n_small);
 #ifdef PTB_BVH_PREFETCH  // both children towards L1 while this node's boxes are tested
     if (left >= 0)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.qnodes + left));

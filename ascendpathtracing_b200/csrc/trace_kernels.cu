@@ -194,6 +194,7 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
     __device__ __forceinline__ void reduce_slot(unsigned int parity) {
         const unsigned int first = parity ? chunk_odd : chunk_even;
         if (first < count) {  // warp-uniform
+            PTB_CHECK(first % kChunkPaths == 0 && (count - first >= kChunkPaths || ((count - first) & ((1u << c_fuse.log2_s) - 1u)) == 0u));
             __syncwarp();     // the lanes' parked colours are visible to the whole warp
             fuse_reduce_chunk(c_fuse.scratch + (scratch + parity * kChunkPaths), first, count - first < kChunkPaths ? count - first : kChunkPaths, lane);
         }
@@ -242,6 +243,7 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
         }
         const unsigned int seq = issued * 32u + lane;
         const unsigned int path = path_of(seq);
+        PTB_CHECK(issued * 32u - head <= static_cast<unsigned int>(kRing) - 32u);  // the batch being written is not one still to be read
         if (path < count) {
             const unsigned int s = seq & (kRing - 1);
             if (GEN) {
@@ -271,6 +273,7 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
             __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
         __syncwarp();                  // ... and is visible to the other lanes of the warp
         slot = ring + (seq & (kRing - 1));
+        PTB_CHECK(!got || (seq < issued * 32u && issued * 32u - seq <= static_cast<unsigned int>(kRing)));  // issued, and not yet overwritten
         head += __popc(wmask);
         if (FUSE)
             head = min(head, issued * 32u);
@@ -321,10 +324,12 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
             if (active && want) {  // lanes that finished a path in the previous iteration
                 if (FUSE) {        // parked for the warp's own resolve (fuse_reduce_chunk)
                     float *park = feed.park(mine);
+                    PTB_CHECK(feed.path_of(mine) < count && mine < feed.head && mine / kChunkPaths + 2u >= (feed.issued + kChunkBatches - 1) / kChunkBatches);  // its chunk has not been reduced yet: the slot is still its chunk's
                     park[0 * kChunkPaths] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
                     park[2 * kChunkPaths] = __fmul_rn(p.rg, scale);
                     park[4 * kChunkPaths] = __fmul_rn(p.rb, scale);
                 } else {
+                    PTB_CHECK(mine < count);
                     pl.col[0][mine] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
                     pl.col[1][mine] = __fmul_rn(p.rg, scale);
                     pl.col[2][mine] = __fmul_rn(p.rb, scale);
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
         float tmin;
         int idx;
         nearest_hit<NS>(p, nsph, one, kEps, tmin, idx);
+        PTB_CHECK(idx >= 0 && idx < nsph);
         bounce_and_shade<EARLY>(p, tmin, idx, light, sh);
         bounce++;
         want = active && ((bounce >= depth) || (EARLY && path_settled(p, zero_stop)));
@@ -405,6 +411,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
                     float *park = feed.park(mine_seq);
                     park[0 * kChunkPaths] = p.lr, park[2 * kChunkPaths] = p.lg, park[4 * kChunkPaths] = p.lb;
                 } else {
+                    PTB_CHECK(mine < count);
                     pl.col[0][mine] = p.lr;
                     pl.col[1][mine] = p.lg;
                     pl.col[2][mine] = p.lb;
@@ -495,6 +502,7 @@ struct HybridStack {
     int sp;
     __device__ __forceinline__ void push_if(bool c, int x) {
         const bool fast = c && sp < kShortStack;
+        PTB_CHECK(!c || (sp >= 0 && sp < kBvhStack));
         if (fast)
             s[sp * kTraceThreads] = x;
         if (c && !fast)
@@ -578,12 +586,14 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
         const unsigned int fmask = __ballot_sync(0xffffffffu, fin);
         if (fmask != 0u) {
             if (fin) {
+                PTB_CHECK(slot >= 0 && slot < kPool && sq_count + __popc(fmask & lt) < kPool);
                 pool.tmin[slot] = tmin;
                 pool.idx[slot] = idx;
                 pool.sq[sq_count + __popc(fmask & lt)] = static_cast<unsigned char>(slot);
                 cur = false;
             }
             sq_count += __popc(fmask);
+            PTB_CHECK(sq_count + tq_count + __popc(__ballot_sync(0xffffffffu, cur)) <= kPool);  // a slot is in at most one place (fewer at the very end)
             __syncwarp();
         }
         const unsigned int busy = __ballot_sync(0xffffffffu, cur);
@@ -594,6 +604,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
             int s2 = 0;
             if (has)
                 s2 = pool.sq[sq_count - n_take + lane];
+            PTB_CHECK(s2 >= 0 && s2 < kPool);
             sq_count -= n_take;
             MatPath p;
             p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -614,6 +625,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
                 const unsigned long long pid = (GEN && c_gen.x_step > 1) ? strided_global_path(c_gen, mypath) : path0 + mypath;
                 ended = material_shade<true>(p, pool.tmin[s2], pool.idx[s2], rr_start, seed, pid, nosh, bvh) || p.depth >= max_depth;
                 if (ended) {
+                    PTB_CHECK(mypath < count);
                     pl.col[0][mypath] = p.lr;
                     pl.col[1][mypath] = p.lg;
                     pl.col[2][mypath] = p.lb;
@@ -637,6 +649,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
                 }
                 const unsigned int path = rank < avail ? next + rank : fresh + (rank - avail);
                 got = need && (rank < avail || path < fresh_end);
+                PTB_CHECK(!got || path < count);
                 if (n_need > avail) {
                     next = fresh + (n_need - avail);
                     chunk_end = fresh_end;
@@ -680,6 +693,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
                 pool.idx[s2] = i;
             }
             const unsigned int cmask = __ballot_sync(0xffffffffu, cont);
+            PTB_CHECK(tq_count + __popc(cmask) <= kPool);
             if (cont)
                 pool.tq[tq_count + __popc(cmask & lt)] = static_cast<unsigned char>(s2);
             tq_count += __popc(cmask);
@@ -693,6 +707,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
             bool exact_loop = false;  // a ray the quantised walk does not cover (pt_bvh.cuh): every sphere, by the whole warp
             if (!cur && rank < tq_count) {
                 slot = pool.tq[tq_count - 1 - rank];
+                PTB_CHECK(slot >= 0 && slot < kPool);
                 ox = pool.ray[0][slot], oy = pool.ray[1][slot], oz = pool.ray[2][slot];
                 dx = pool.ray[3][slot], dy = pool.ray[4][slot], dz = pool.ray[5][slot];
                 tmin = pool.tmin[slot];
