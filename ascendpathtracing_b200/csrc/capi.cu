@@ -49,8 +49,8 @@ int check_params(const PtParams *p, const char *who) {
         return fail(PTB200_EINVAL, "%s: params is NULL", who);
     if (p->width < 1 || p->height < 1 || p->samples < 1)
         return fail(PTB200_EINVAL, "%s: width/height/samples must be >= 1 (got %d x %d x %d)", who, p->width, p->height, p->samples);
-    if (p->depth < 1)
-        return fail(PTB200_EINVAL, "%s: depth must be >= 1 (got %d)", who, p->depth);
+    if (p->depth < 1 || p->depth > 0xffffff)  // the kernels count a path's bounces in 24 bits of its lane's state word
+        return fail(PTB200_EINVAL, "%s: depth must be in [1, 16777215] (got %d)", who, p->depth);
     if (p->sphere_count < 1 || p->sphere_count > 1024)
         return fail(PTB200_EINVAL, "%s: sphere_count must be in [1, 1024] for the brute-force kernel (got %d)", who, p->sphere_count);
     if (p->sphere_stride < p->sphere_count)

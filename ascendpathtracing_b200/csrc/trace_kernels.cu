@@ -23,7 +23,7 @@ namespace ptb200 {
 // ---- scene staging: device SoA [10][stride] -> constant bank -------------------------------------
 // Writes through the global-memory alias of the __constant__ symbols (cudaGetSymbolAddress); the
 // constant cache is coherent across kernel launches, and launches on one stream are ordered.
-__global__ void pack_scene_kernel(const float *__restrict__ spheres, int nsph, int stride, SceneConst *dst, int *zero_ok) {
+__global__ void pack_scene_kernel(const float *__restrict__ spheres, int nsph, int stride, SceneConst *dst, int *zero_ok, float *zero_or_nan) {
     __shared__ int ok;
     if (threadIdx.x == 0)
         ok = 1;
@@ -46,8 +46,10 @@ __global__ void pack_scene_kernel(const float *__restrict__ spheres, int nsph, i
             ok = 0;
     }
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         *zero_ok = ok;
+        *zero_or_nan = ok ? 0.0f : __int_as_float(0x7fc00000);
+    }
 }
 
 // ---- the trace kernel -----------------------------------------------------------------------------
@@ -61,6 +63,12 @@ struct TracePlanes {
 
 constexpr int kRingBatches = 4;                  // batches of 32 rays in the ring per warp (power of two)
 constexpr int kRing = 32 * kRingBatches;         // ring entries per warp
+// Ring layout.  Fused generation (GEN): one entry = one ray as 8 floats (ox oy oz dx | dy dz - -): the generator stores it with
+// one STS.128 + one STS.64 and a lane picks it up with one LDS.128 + one LDS.64.  Ray files: six planes of kRing floats, because
+// the ring is filled by 4-byte cp.async copies from six global planes and entry-major rows would put the 32 lanes of a copy
+// on 8 banks (measured: entry-major costs the ray-file kernel 1.4 %, and saves the fused kernel 3 %).  Same footprint either way.
+constexpr int kRingEntry = 8;
+constexpr int kRingFloats = kRing * kRingEntry;   // per warp (the plane-major layout uses 6/8 of it)
 constexpr int kWarpsPerBlock = kTraceThreads / 32;
 
 // A warp claims this many batches of 32 consecutive paths at a time (>= kRingBatches).  The last chunk a warp claims is
@@ -84,9 +92,8 @@ static __constant__ RayGenSource c_gen;
 static __device__ __noinline__ void generate_ray_to_ring(unsigned int path, float *slot) {
     float r[6];
     generate_ray(c_gen, static_cast<long long>(path), r);
-#pragma unroll
-    for (int c = 0; c < 6; c++)
-        slot[c * kRing] = r[c];
+    *reinterpret_cast<float4 *>(slot) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float2 *>(slot + 4) = make_float2(r[4], r[5]);
 }
 
 // ---- fused resolve (FUSE): the production entries never materialise per-path colours ------------------------------------
@@ -247,7 +254,7 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
         if (path < count) {
             const unsigned int s = seq & (kRing - 1);
             if (GEN) {
-                generate_ray_to_ring(path, ring + s);
+                generate_ray_to_ring(path, ring + s * kRingEntry);
             } else {
 #pragma unroll
                 for (int c = 0; c < 6; c++)
@@ -260,7 +267,7 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
         return rearm;
     }
     // Called by the whole warp when at least one lane wants a path.  Lanes that get one receive its index and a pointer
-    // to its ray in the ring (component c at slot[c * kRing]); the caller reads it and then calls refill().
+    // to its ray in the ring (load_ray(slot, ...)); the caller reads it and then calls refill().
     // seq: the path's warp-local sequence number (FUSE parks its colour by it).  FUSE never hands out a sequence number that has
     // not been issued (the ring can run dry behind a postponed chunk claim).
     __device__ __forceinline__ bool take(bool want, unsigned int wmask, unsigned int &path, unsigned int &seq, const float *&slot) {
@@ -272,7 +279,7 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
         if (!GEN)
             __pipeline_wait_prior(1);  // everything but the newest batch has landed ...
         __syncwarp();                  // ... and is visible to the other lanes of the warp
-        slot = ring + (seq & (kRing - 1));
+        slot = ring + (seq & (kRing - 1)) * (GEN ? kRingEntry : 1);
         PTB_CHECK(!got || (seq < issued * 32u && issued * 32u - seq <= static_cast<unsigned int>(kRing)));  // issued, and not yet overwritten
         head += __popc(wmask);
         if (FUSE)
@@ -287,6 +294,17 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
     }
 };
 
+template <bool GEN> __device__ __forceinline__ void load_ray(const float *slot, float &ox, float &oy, float &oz, float &dx, float &dy, float &dz) {
+    if (GEN) {
+        const float4 a = *reinterpret_cast<const float4 *>(slot);
+        const float2 b = *reinterpret_cast<const float2 *>(slot + 4);
+        ox = a.x, oy = a.y, oz = a.z, dx = a.w, dy = b.x, dz = b.y;
+    } else {
+        ox = slot[0 * kRing], oy = slot[1 * kRing], oz = slot[2 * kRing];
+        dx = slot[3 * kRing], dy = slot[4 * kRing], dz = slot[5 * kRing];
+    }
+}
+
 #ifndef PTB_BLOCKS_PER_SM
 #define PTB_BLOCKS_PER_SM 5
 #endif
@@ -296,6 +314,111 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
                                                                        unsigned long long *__restrict__ stats, unsigned long long *work_counter) {
     extern __shared__ float4 smem[];
     SceneShared sh;
+#ifndef PTB_OLD_LOOP
+    // Shared memory: [block-level tables (generic sphere count only)][per warp: ring, then -- 8-sphere kernels -- the warp's own copy
+    // of the two lookup tables, so that ring and tables hang off ONE per-warp base register (the block-level table base was
+    // rematerialised from S2UR / ULEA every bounce)].
+    float *const wsm = reinterpret_cast<float *>(smem + (NS > 0 ? 0 : 2 * nsph)) + (threadIdx.x >> 5) * (kRingFloats + (NS > 0 ? 8 * NS : 0));
+    if (NS > 0) {
+        sh.center = reinterpret_cast<float4 *>(wsm + kRingFloats);
+        sh.color = sh.center + NS;
+        const int k = static_cast<int>(threadIdx.x & 31u);
+        if (k < NS) {
+            sh.center[k] = make_float4(spheres[1 * stride + k], spheres[2 * stride + k], spheres[3 * stride + k], 0.0f);
+            sh.color[k] = (EARLY && k == light) ? make_float4(1.0f, 1.0f, 1.0f, 1.0f)
+                                                : make_float4(spheres[7 * stride + k], spheres[8 * stride + k], spheres[9 * stride + k], 0.0f);
+        }
+        __syncwarp();
+    } else {
+        stage_scene_shared(smem, spheres, nsph, stride, sh, EARLY ? light : -1);
+    }
+    // Persistent warps with path regeneration.  The loop body is exactly one bounce, so the lanes of a warp may be at
+    // different bounces of different paths without diverging.  Lanes whose path finished are ranked by a ballot and take
+    // the next consecutive paths of the warp's current chunk, so the rays they fetch and (to within the few paths in
+    // flight) the colours they store share cache lines.  See PathFeeder for how paths reach the warp.
+    //
+    // A lane's whole control state is ONE integer, so that the per-bounce bookkeeping is a compare, a vote and two integer
+    // instructions (the first version kept `active` / `want` / `alive` flags in registers and spent ~36 of ~290 instructions per
+    // bounce moving them in and out of predicates, profiles/r2_trace_lean_loop.md):
+    //   0 <= bounce < depth   the lane holds a path that has done `bounce` bounces
+    //   bounce >= depth       the path is finished: depth reached, or settled early (kFin added: the count stays in the low bits)
+    //   kNoStore              the lane wants a path and has no colour to store (launch start; FUSE: after a postponed claim)
+    //   negative (kIdle + k)  no path, no more work: k <= depth more iterations pass before the warp leaves
+    constexpr int kFin = 0x40000000, kNoStore = 0x20000000, kIdle = static_cast<int>(0x80000000u), kCountMask = 0x00ffffff;
+    // "throughput is exactly (0,0,0)" is only a stop when the scene allows it (pack_scene_kernel): otherwise compare with NaN
+    const unsigned int lane = threadIdx.x & 31u;
+    PathFeeder<GEN, FUSE> feed(pl, wsm, work_counter, count, lane);
+
+    PathState p;
+    p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
+    p.dz = 1.0f;
+    p.rr = p.rg = p.rb = 1.0f;
+    p.alive = true;
+    int bounce = kNoStore;
+    unsigned int segs = 0;
+    unsigned int mine = 0;      // path this lane holds (FUSE: its warp-local sequence number)
+
+    for (;;) {
+        const bool want = bounce >= depth;
+        const unsigned int wmask = __ballot_sync(0xffffffffu, want);
+        if (wmask != 0u) {  // warp-uniform
+            if (want && bounce != kNoStore) {  // lanes that finished a path in the previous iteration
+                if (FUSE) {                    // parked for the warp's own resolve (fuse_reduce_chunk)
+                    float *park = feed.park(mine);
+                    PTB_CHECK(feed.path_of(mine) < count && mine < feed.head && mine / kChunkPaths + 2u >= (feed.issued + kChunkBatches - 1) / kChunkBatches);  // its chunk has not been reduced yet: the slot is still its chunk's
+                    park[0 * kChunkPaths] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
+                    park[2 * kChunkPaths] = __fmul_rn(p.rg, scale);
+                    park[4 * kChunkPaths] = __fmul_rn(p.rb, scale);
+                } else {
+                    PTB_CHECK(mine < count);
+                    pl.col[0][mine] = __fmul_rn(p.rr, scale);  // render.cpp:194-196
+                    pl.col[1][mine] = __fmul_rn(p.rg, scale);
+                    pl.col[2][mine] = __fmul_rn(p.rb, scale);
+                }
+                segs += static_cast<unsigned int>(bounce & kCountMask);
+            }
+            unsigned int path, seq;
+            const float *slot;
+            const bool got = feed.take(want, wmask, path, seq, slot);
+            if (got) {
+                load_ray<GEN>(slot, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz);
+                mine = FUSE ? seq : path;
+            }
+            const bool rearm = feed.refill(want ? got : bounce >= 0, mine);  // warp-uniform; FUSE only, and next to never
+            if (want) {
+                bounce = got ? 0 : kIdle;
+                p.rr = p.rg = p.rb = 1.0f;
+                p.alive = true;
+            }
+            if (FUSE && rearm) {
+                if (bounce < 0)
+                    bounce = kNoStore;
+                continue;
+            }
+            if (!__any_sync(0xffffffffu, bounce >= 0))
+                break;
+        }
+        float tmin;
+        int idx;
+        nearest_hit<NS>(p, nsph, one, kEps, tmin, idx);
+        PTB_CHECK(idx >= 0 && idx < nsph);
+        if (EARLY) {
+            // exact early termination: the light reached (every later factor is exactly 1) or the throughput exactly (+0,+0,+0)
+            const bool lit = bounce_and_shade_early(p, tmin, idx, sh);
+            bool settled = lit;
+            if (fmaxf(fmaxf(p.rr, p.rg), p.rb) == c_scene_zero_or_nan)
+                settled = true;
+            bounce++;
+            if (settled)
+                bounce |= kFin;  // OR, not +: an idle lane (negative) shades garbage and must stay negative
+        } else {
+            bounce_and_shade<false>(p, tmin, idx, light, sh);
+            bounce++;
+        }
+    }
+    if (FUSE)
+        feed.finish();
+#else
     stage_scene_shared(smem, spheres, nsph, stride, sh);
     const bool zero_stop = c_scene_zero_stop_ok != 0;
 
@@ -305,7 +428,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
     // flight) the colours they store share cache lines.  See PathFeeder for how paths reach the warp.
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    PathFeeder<GEN, FUSE> feed(pl, reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
+    PathFeeder<GEN, FUSE> feed(pl, reinterpret_cast<float *>(smem + 2 * nsph) + warp_in_block * kRingFloats, work_counter, count, lane);
 
     PathState p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -340,8 +463,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
             const float *slot;
             const bool got = feed.take(want, wmask, path, seq, slot);
             if (got) {
-                p.ox = slot[0 * kRing], p.oy = slot[1 * kRing], p.oz = slot[2 * kRing];
-                p.dx = slot[3 * kRing], p.dy = slot[4 * kRing], p.dz = slot[5 * kRing];
+                load_ray<GEN>(slot, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz);
                 mine = FUSE ? seq : path;
             }
             const bool rearm = feed.refill(want ? got : active, mine);  // warp-uniform; FUSE only, and next to never
@@ -369,6 +491,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
     }
     if (FUSE)
         feed.finish();
+#endif
     if (stats != nullptr) {
         unsigned int w = segs;
 #pragma unroll
@@ -392,7 +515,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
     stage_materials_shared(smem, spheres, nsph, stride, sh);
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int warp_in_block = threadIdx.x >> 5;
-    PathFeeder<GEN, FUSE> feed(pl, reinterpret_cast<float *>(smem + 3 * nsph) + warp_in_block * (6 * kRing), work_counter, count, lane);
+    PathFeeder<GEN, FUSE> feed(pl, reinterpret_cast<float *>(smem + 3 * nsph) + warp_in_block * kRingFloats, work_counter, count, lane);
 
     MatPath p;
     p.ox = p.oy = p.oz = p.dx = p.dy = 0.0f;
@@ -421,8 +544,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
             const float *slot;
             const bool got = feed.take(want, wmask, path, seq, slot);
             if (got) {
-                p.ox = slot[0 * kRing], p.oy = slot[1 * kRing], p.oz = slot[2 * kRing];
-                p.dx = slot[3 * kRing], p.dy = slot[4 * kRing], p.dz = slot[5 * kRing];
+                load_ray<GEN>(slot, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz);
                 mine = path;
                 mine_seq = seq;
             }
@@ -789,6 +911,7 @@ struct DeviceState {
     int blocks_per_sm[16] = {};  // [FUSE?][GEN?][NS8?][EARLY?]
     SceneConst *scene_alias = nullptr;
     int *zero_ok_alias = nullptr;
+    float *zero_or_nan_alias = nullptr;
     unsigned long long *work_counter = nullptr;  // chunk dispenser of the persistent kernels (reset before every launch)
     float *fuse_scratch = nullptr;     // fused resolve: kFuseScratchFloats per warp of the largest grid launched so far
     size_t fuse_scratch_warps = 0;
@@ -850,6 +973,8 @@ cudaError_t ensure_device_state(DeviceState **out) {
             return e;
         if ((e = cudaGetSymbolAddress(reinterpret_cast<void **>(&s.zero_ok_alias), c_scene_zero_stop_ok)) != cudaSuccess)
             return e;
+        if ((e = cudaGetSymbolAddress(reinterpret_cast<void **>(&s.zero_or_nan_alias), c_scene_zero_or_nan)) != cudaSuccess)
+            return e;
         if ((e = cudaEventCreateWithFlags(&s.scene_free, cudaEventDisableTiming)) != cudaSuccess)
             return e;
         if ((e = cudaMalloc(reinterpret_cast<void **>(&s.work_counter), sizeof(unsigned long long))) != cudaSuccess)
@@ -878,7 +1003,13 @@ template <int NS, bool EARLY, bool GEN, bool FUSE = false>
 cudaError_t launch_trace(DeviceState &s, cudaStream_t stream, const float *rays, const float *spheres, float *colors, int64_t n,
                          int64_t first, int64_t count, const PtParams &p, unsigned long long *stats, const RayGenSource *gen,
                          const FuseTarget *fuse = nullptr) {
-    const size_t smem = sizeof(float4) * 2 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
+#ifndef PTB_OLD_LOOP
+    // 8-sphere kernels: every warp holds its own copy of the lookup tables behind its ring (trace_paths_kernel)
+    const size_t smem = NS > 0 ? sizeof(float) * (kRingFloats + 8 * NS) * kWarpsPerBlock
+                               : sizeof(float4) * 2 * static_cast<size_t>(p.sphere_count) + sizeof(float) * kRingFloats * kWarpsPerBlock;
+#else
+    const size_t smem = sizeof(float4) * 2 * static_cast<size_t>(p.sphere_count) + sizeof(float) * kRingFloats * kWarpsPerBlock;
+#endif
     int &occ = s.blocks_per_sm[(FUSE ? 8 : 0) + (GEN ? 4 : 0) + (NS > 0 ? 2 : 0) + (EARLY ? 1 : 0)];
     if (occ == 0 || NS == 0) {
         cudaError_t e = cudaSuccess;
@@ -946,7 +1077,7 @@ cudaError_t trace_paths(cudaStream_t stream, const PtParams &p, const float *ray
         if ((e = cudaStreamWaitEvent(stream, s->scene_free, 0)) != cudaSuccess)
             return e;
     }
-    pack_scene_kernel<<<1, 128, 0, stream>>>(spheres, p.sphere_count, p.sphere_stride, s->scene_alias, s->zero_ok_alias);
+    pack_scene_kernel<<<1, 128, 0, stream>>>(spheres, p.sphere_count, p.sphere_stride, s->scene_alias, s->zero_ok_alias, s->zero_or_nan_alias);
     if ((e = cudaGetLastError()) != cudaSuccess)
         return e;
     // Early termination and the fixed-depth loop give identical bits, so which one runs is a pure performance choice:
@@ -1012,13 +1143,13 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
             return e;
     }
     if (p.sphere_count > 0) {
-        pack_scene_kernel<<<1, 128, 0, stream>>>(spheres, p.sphere_count, p.sphere_stride, s->scene_alias, s->zero_ok_alias);
+        pack_scene_kernel<<<1, 128, 0, stream>>>(spheres, p.sphere_count, p.sphere_stride, s->scene_alias, s->zero_ok_alias, s->zero_or_nan_alias);
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }
     const bool use_tree = tree != nullptr;
     const size_t smem = use_tree ? sizeof(WarpPool) * kWarpsPerBlock + sizeof(int) * kShortStack * kTraceThreads
-                                 : sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count) + sizeof(float) * 6 * kRing * kWarpsPerBlock;
+                                 : sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count) + sizeof(float) * kRingFloats * kWarpsPerBlock;
     const bool ten = !use_tree && (p.sphere_count == 9 || p.sphere_count == 10);  // smallpt's scene: unrolled pairs (index 9 is padding)
     if (use_tree && smem > 48 * 1024) {  // only with non-default pool / stack sizes: opt in to more than 48 KB per block
         if ((e = cudaFuncSetAttribute(trace_materials_bvh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess ||
