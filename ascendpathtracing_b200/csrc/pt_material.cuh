@@ -35,6 +35,10 @@ __device__ __forceinline__ void stage_materials_shared(float4 *smem, const float
     __syncthreads();
 }
 
+// The ten Philox round keys of the material seed, staged per launch next to the scene (trace_materials): the kernels XOR them in
+// straight from the constant bank instead of running the key schedule (20 integer adds) at every bounce.
+static __constant__ PhiloxKeys c_mat_keys;
+
 struct MatPath {
     float ox, oy, oz, dx, dy, dz;
     float tr, tg, tb;  // throughput
@@ -93,7 +97,8 @@ __device__ __forceinline__ bool material_shade(MatPath &p, float tmin, int idx, 
     if (!(tmin < kMiss))
         return true;
     uint32_t w[4] = {static_cast<uint32_t>(path), static_cast<uint32_t>(path >> 32), static_cast<uint32_t>(p.depth), 0x4d41u};
-    philox4x32_10(w, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    (void)seed;
+    philox4x32_10_keyed(w, c_mat_keys);  // == philox4x32_10(w, lo(seed), hi(seed))
     const float u1 = __fmul_rn(static_cast<float>(w[0] >> 8), 5.9604645e-8f), u2 = __fmul_rn(static_cast<float>(w[1] >> 8), 5.9604645e-8f);
     const float u3 = __fmul_rn(static_cast<float>(w[2] >> 8), 5.9604645e-8f), u4 = __fmul_rn(static_cast<float>(w[3] >> 8), 5.9604645e-8f);
 

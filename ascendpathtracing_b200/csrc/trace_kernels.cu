@@ -1147,6 +1147,11 @@ cudaError_t trace_materials(cudaStream_t stream, const PtParams &p_in, const PtM
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }
+    {   // the material RNG's round keys (same stream ordering as the scene: the previous launch sequence has been waited for)
+        const PhiloxKeys keys = philox_keys(mp.seed);
+        if ((e = cudaMemcpyToSymbolAsync(c_mat_keys, &keys, sizeof keys, 0, cudaMemcpyHostToDevice, stream)) != cudaSuccess)
+            return e;
+    }
     const bool use_tree = tree != nullptr;
     const size_t smem = use_tree ? sizeof(WarpPool) * kWarpsPerBlock + sizeof(int) * kShortStack * kTraceThreads
                                  : sizeof(float4) * 3 * static_cast<size_t>(p.sphere_count) + sizeof(float) * kRingFloats * kWarpsPerBlock;
