@@ -71,8 +71,8 @@ int check_device(const char *who) {
 int check_material_params(const PtMaterialParams *mp, const char *who) {
     if (mp == nullptr)
         return fail(PTB200_EINVAL, "%s: material params is NULL", who);
-    if (mp->max_depth < 1 || mp->rr_start < 0 || !(mp->hit_epsilon > 0.0f))
-        return fail(PTB200_EINVAL, "%s: need max_depth >= 1, rr_start >= 0, hit_epsilon > 0", who);
+    if (mp->max_depth < 1 || mp->max_depth > 0xffffff || mp->rr_start < 0 || !(mp->hit_epsilon > 0.0f))
+        return fail(PTB200_EINVAL, "%s: need 1 <= max_depth <= 16777215, rr_start >= 0, hit_epsilon > 0", who);
     return PTB200_OK;
 }
 

@@ -524,12 +524,16 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
     p.lr = p.lg = p.lb = 0.0f;
     p.depth = 0;
     unsigned int segs = 0, mine = 0, mine_seq = 0;
-    bool active = false, want = true;
+    // one integer of lane state, as in trace_paths_kernel: 0 <= state < max_depth running (= p.depth); >= max_depth finished (kFin
+    // OR-ed in when the path ended before the cap); kNoStore wants a path, nothing to store; negative idle
+    constexpr int kFin = 0x40000000, kNoStore = 0x20000000, kIdle = static_cast<int>(0x80000000u);
+    int state = kNoStore;
 
     for (;;) {
+        const bool want = state >= max_depth;
         const unsigned int wmask = __ballot_sync(0xffffffffu, want);
         if (wmask != 0u) {
-            if (active && want) {
+            if (want && state != kNoStore) {
                 if (FUSE) {  // parked for the warp's own resolve (fuse_reduce_chunk)
                     float *park = feed.park(mine_seq);
                     park[0 * kChunkPaths] = p.lr, park[2 * kChunkPaths] = p.lg, park[4 * kChunkPaths] = p.lb;
@@ -548,27 +552,27 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_materials_kernel(const
                 mine = path;
                 mine_seq = seq;
             }
-            const bool rearm = feed.refill(want ? got : active, mine_seq);  // warp-uniform; FUSE only, and next to never
+            const bool rearm = feed.refill(want ? got : state >= 0, mine_seq);  // warp-uniform; FUSE only, and next to never
             if (want) {
-                active = got;
+                state = got ? 0 : kIdle;
                 p.tr = p.tg = p.tb = 1.0f;
                 p.lr = p.lg = p.lb = 0.0f;
-                p.depth = 0;
-                want = false;
             }
             if (FUSE && rearm) {
-                want = !active;
+                if (state < 0)
+                    state = kNoStore;
                 continue;
             }
-            if (!__any_sync(0xffffffffu, active))
+            if (!__any_sync(0xffffffffu, state >= 0))
                 break;
         }
-        if (active) {  // dead lanes of a finished range idle; live ones diverge by material inside
+        if (state >= 0) {  // idle lanes of a finished range wait; live ones diverge by material inside
             segs++;
+            p.depth = state;
             // RNG key: the global path index (a strided launch walks a dense frame of every k-th column, pt_raygen.cuh)
             const unsigned long long pid = (GEN && c_gen.x_step > 1) ? strided_global_path(c_gen, mine) : path0 + mine;
             const bool ended = material_bounce<NS>(p, nsph, one, eps, rr_start, seed, pid, sh);
-            want = ended || p.depth >= max_depth;
+            state = ended ? (p.depth | kFin) : p.depth;
         }
     }
     if (FUSE)
