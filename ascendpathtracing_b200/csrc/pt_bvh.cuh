@@ -121,12 +121,23 @@ __device__ __forceinline__ BvhRay bvh_ray(const BvhScene &sc, float ox, float oy
 // Slab test of one quantised child box.  NaN planes (0 * inf, inf - inf on an axis the ray does not move along) drop out
 // of the 3-input min/max, which only makes the test more permissive.
 __device__ __forceinline__ bool hit_qbox(const BvhRay &r, unsigned int wx, unsigned int wy, unsigned int wz, float tbest, float &tnear) {
+#ifdef PTB_BVH_SCALAR_SLABS
     const float nx = __fmaf_rn(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx)), r.idx, r.nx);
     const float ny = __fmaf_rn(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy)), r.idy, r.ny);
     const float nz = __fmaf_rn(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz)), r.idz, r.nz);
     const float fx = __fmaf_rn(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx ^ 0x22u)), r.idx, r.fx);
     const float fy = __fmaf_rn(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy ^ 0x22u)), r.idy, r.fy);
     const float fz = __fmaf_rn(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz ^ 0x22u)), r.idz, r.fz);
+#else
+    // near and far plane of an axis as one packed FFMA2 (same two roundings as two FFMAs, half the issue slots)
+    const float2 px = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx)), __uint_as_float(__byte_perm(wx, 0x4B000000u, r.sx ^ 0x22u))),
+                                 make_float2(r.idx, r.idx), make_float2(r.nx, r.fx));
+    const float2 py = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy)), __uint_as_float(__byte_perm(wy, 0x4B000000u, r.sy ^ 0x22u))),
+                                 make_float2(r.idy, r.idy), make_float2(r.ny, r.fy));
+    const float2 pz = __ffma2_rn(make_float2(__uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz)), __uint_as_float(__byte_perm(wz, 0x4B000000u, r.sz ^ 0x22u))),
+                                 make_float2(r.idz, r.idz), make_float2(r.nz, r.fz));
+    const float nx = px.x, ny = py.x, nz = pz.x, fx = px.y, fy = py.y, fz = pz.y;
+#endif
     const float tn = fmaxf(fmaxf(nx, ny), nz);
     const float tf = fminf(fminf(fx, fy), fz);
     tnear = tn;
