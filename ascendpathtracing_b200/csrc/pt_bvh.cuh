@@ -180,7 +180,7 @@ __device__ __forceinline__ void bvh_leaf(const BvhScene &sc, int sphere, float o
 // One traversal step at internal node `node`: tests both child boxes, reports hit leaves in leaf_a / leaf_b (sphere index
 // or -1; leaf_b is only set when leaf_a is) and leaves the next internal node in `node` (-1 when the stack ran empty:
 // traversal finished).  The caller runs the exact test on the leaves -- at once, or batched across the warp.
-// Stack: push_if(bool, int), int pop_if(bool, int fallback) -- predicated, no branches on the common path.
+// Stack: int step(bool push, bool pop, int x, int otherwise) -- a traversal step pushes x, pops (-1 when empty), or neither.
 template <class Stack>
 __device__ __forceinline__ void bvh_step_boxes(const BvhScene &sc, const BvhRay &r, float tmin, int &node, int &leaf_a, int &leaf_b, Stack &st) {
     uint4 L, R;
@@ -203,9 +203,8 @@ __device__ __forceinline__ void bvh_step_boxes(const BvhScene &sc, const BvhRay 
     const bool hl = bl && left >= 0, hr = br && right >= 0;
     // near child first, far child on the stack; nothing hit: pop
     const bool lfirst = tl <= tr, both = hl && hr;
-    st.push_if(both, lfirst ? right : left);
-    const int next = both ? (lfirst ? left : right) : (hl ? left : right);
-    node = st.pop_if(!(hl || hr), next);
+    const int next = (both ? lfirst : hl) ? left : right;
+    node = st.step(both, !(hl || hr), lfirst ? right : left, next);
 }
 
 // Step with the leaves tested at once (the plain per-lane walk).
@@ -262,6 +261,10 @@ struct LocalStack {  // per-lane stack in local memory
         if (!c)
             return fallback;
         return sp == 0 ? -1 : v[--sp];
+    }
+    __device__ __forceinline__ int step(bool push, bool pop, int x, int otherwise) {  // a step pushes, pops, or neither
+        push_if(push, x);
+        return pop_if(pop, otherwise);
     }
 };
 

@@ -622,27 +622,41 @@ struct WarpPool {
     unsigned char tq[kPool], sq[kPool];
 };
 
+// Traversal stack of one lane: kShortStack entries in shared memory (entry k of lane t at s32 + 4 * (k * kTraceThreads + t):
+// conflict-free columns), deeper entries in local memory (deep, unbalanced trees only: a branch, not predicated code, because it
+// next to never runs).  A traversal step either pushes (both children hit), pops (none hit) or neither, so push and pop share one
+// address; the base is a 32-bit shared-window address made opaque to the compiler, which otherwise rematerialises it from
+// S2R / S2UR / ULEA at every step (6 instructions).
 struct HybridStack {
-    int *s;    // this lane's column in shared memory: entry k at s[k * kTraceThreads]
-    int *ovf;  // local memory, entries kShortStack and up (deep, unbalanced trees only)
+    unsigned int s32;  // shared-window byte address of this lane's column
+    int *ovf;          // local memory, entries kShortStack and up
     int sp;
-    __device__ __forceinline__ void push_if(bool c, int x) {
-        const bool fast = c && sp < kShortStack;
-        PTB_CHECK(!c || (sp >= 0 && sp < kBvhStack));
-        if (fast)
-            s[sp * kTraceThreads] = x;
-        if (c && !fast)
-            ovf[sp - kShortStack] = x;
-        sp += c ? 1 : 0;
+    __device__ __forceinline__ void init(int *column, int *overflow) {
+        s32 = static_cast<unsigned int>(__cvta_generic_to_shared(column));
+        asm volatile("mov.u32 %0, %0;" : "+r"(s32));
+        ovf = overflow;
+        sp = 0;
     }
-    __device__ __forceinline__ int pop_if(bool c, int fallback) {
-        const bool have = c && sp > 0;
-        sp -= have ? 1 : 0;
-        int v = c ? -1 : fallback;
-        if (have && sp < kShortStack)
-            v = s[sp * kTraceThreads];
-        if (have && sp >= kShortStack)
-            v = ovf[sp - kShortStack];
+    // push x (push), or pop into the return value (pop; -1 when the stack is empty), or return `otherwise`
+    __device__ __forceinline__ int step(bool push, bool pop, int x, int otherwise) {
+        const int k = pop ? sp - 1 : sp;  // the entry touched
+        int v = otherwise;
+        if (pop)
+            v = -1;
+        const unsigned int a = s32 + static_cast<unsigned int>(k) * (kTraceThreads * 4u);
+        if (k < kShortStack) {
+            if (push)
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+            if (pop && k >= 0)
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+        } else {  // rare
+            PTB_CHECK(k < kBvhStack);
+            if (push)
+                ovf[k - kShortStack] = x;
+            if (pop)
+                v = ovf[k - kShortStack];
+        }
+        sp = push ? sp + 1 : ((pop && k >= 0) ? k : sp);
         return v;
     }
 };
@@ -692,13 +706,15 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
     unsigned int next = 0, chunk_end = 0;  // the warp's current chunk of paths: [next, chunk_end)
     __syncwarp();
 
-    bool cur = false;  // this lane holds a ray (walking, or finished and not yet deposited)
-    int slot = 0, node = -1, idx = 0;
+    // node >= 0: walking, at that internal node; kWalked: holds a ray whose walk is over (hit not yet deposited); kNoRay: free lane
+    constexpr int kWalked = -1, kNoRay = -2;
+    int slot = 0, node = kNoRay, idx = 0;
     int pend = -1;     // a hit leaf whose exact test waits for company (kLeafBatch lanes) or for the next requeue stop
     float tmin = kMiss;
     BvhRay r = {};
     int stack_overflow[kBvhStack - kShortStack];
-    HybridStack st = {reinterpret_cast<int *>(reinterpret_cast<WarpPool *>(smem) + kWarpsPerBlock) + threadIdx.x, stack_overflow, 0};
+    HybridStack st;
+    st.init(reinterpret_cast<int *>(reinterpret_cast<WarpPool *>(smem) + kWarpsPerBlock) + threadIdx.x, stack_overflow);
     unsigned int segs = 0;
 
     for (;;) {
@@ -708,7 +724,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
                      tmin, idx);
             pend = -1;
         }
-        const bool fin = cur && node < 0;
+        const bool fin = node == kWalked;
         const unsigned int fmask = __ballot_sync(0xffffffffu, fin);
         if (fmask != 0u) {
             if (fin) {
@@ -716,13 +732,13 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
                 pool.tmin[slot] = tmin;
                 pool.idx[slot] = idx;
                 pool.sq[sq_count + __popc(fmask & lt)] = static_cast<unsigned char>(slot);
-                cur = false;
+                node = kNoRay;
             }
             sq_count += __popc(fmask);
-            PTB_CHECK(sq_count + tq_count + __popc(__ballot_sync(0xffffffffu, cur)) <= kPool);  // a slot is in at most one place (fewer at the very end)
+            PTB_CHECK(sq_count + tq_count + __popc(__ballot_sync(0xffffffffu, node != kNoRay)) <= kPool);  // a slot is in at most one place (fewer at the very end)
             __syncwarp();
         }
-        const unsigned int busy = __ballot_sync(0xffffffffu, cur);
+        const unsigned int busy = __ballot_sync(0xffffffffu, node != kNoRay);
         // 2. a full warp of hits (or the last few): shade, regenerate, brute-force pass, back to tq
         if (sq_count >= 32 || (sq_count > 0 && busy == 0u && tq_count == 0)) {
             const int n_take = sq_count < 32 ? sq_count : 32;
@@ -831,15 +847,14 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
             const int rank = __popc(imask & lt);
             float ox = 0.0f, oy = 0.0f, oz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 1.0f;
             bool exact_loop = false;  // a ray the quantised walk does not cover (pt_bvh.cuh): every sphere, by the whole warp
-            if (!cur && rank < tq_count) {
+            if (node == kNoRay && rank < tq_count) {
                 slot = pool.tq[tq_count - 1 - rank];
                 PTB_CHECK(slot >= 0 && slot < kPool);
                 ox = pool.ray[0][slot], oy = pool.ray[1][slot], oz = pool.ray[2][slot];
                 dx = pool.ray[3][slot], dy = pool.ray[4][slot], dz = pool.ray[5][slot];
                 tmin = pool.tmin[slot];
                 idx = pool.idx[slot];
-                cur = true;
-                node = -1;
+                node = kWalked;
                 st.sp = 0;
                 if (bvh.n_small == 1) {
                     bvh_leaf(bvh, ~bvh.only_leaf, ox, oy, oz, dx, dy, dz, eps, tmin, idx);
@@ -867,9 +882,9 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
             __syncwarp();
         }
         // 4. walk until kRefillLanes more lanes have finished (or nobody walks any more)
-        const unsigned int act = __ballot_sync(0xffffffffu, cur && node >= 0);
+        const unsigned int act = __ballot_sync(0xffffffffu, node >= 0);
         if (act == 0u) {
-            if (__ballot_sync(0xffffffffu, cur) == 0u && sq_count == 0 && tq_count == 0)
+            if (__ballot_sync(0xffffffffu, node != kNoRay) == 0u && sq_count == 0 && tq_count == 0)
                 break;
             continue;
         }
@@ -877,7 +892,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
         const PoolRay pray = {&pool, slot};
         do {
             int leaf_a = -1, leaf_b = -1;
-            if (cur && node >= 0)
+            if (node >= 0)
                 bvh_step_boxes(bvh, r, tmin, node, leaf_a, leaf_b, st);
             // Exact leaf tests are rare per lane (0.7 per ray) but a warp of 28 walkers meets one every other step, and run
             // at once each costs the whole warp ~30 instructions and a memory round trip for one lane's benefit.  So a hit
@@ -893,7 +908,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BVH_BLOCKS_PER_SM)
                     bvh_leaf(bvh, pend, pray.ox(), pray.oy(), pray.oz(), pray.dx(), pray.dy(), pray.dz(), eps, tmin, idx);
                 pend = -1;
             }
-        } while (__popc(__ballot_sync(0xffffffffu, cur && node >= 0)) > stop_at);
+        } while (__popc(__ballot_sync(0xffffffffu, node >= 0)) > stop_at);
     }
     if (stats != nullptr) {
         unsigned int w = segs;
