@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTB_BLOCKS_PER_SM) trace_paths_
         PTB_CHECK(idx >= 0 && idx < nsph);
         if (EARLY) {
             // exact early termination: the light reached (every later factor is exactly 1) or the throughput exactly (+0,+0,+0)
-            const bool lit = bounce_and_shade_early(p, tmin, idx, sh);
+            const bool lit = bounce_and_shade_early(p, tmin, idx, sh, one);
             bool settled = lit;
             if (fmaxf(fmaxf(p.rr, p.rg), p.rb) == c_scene_zero_or_nan)
                 settled = true;
