@@ -86,7 +86,9 @@ def test_legacy_config_enforces_reference_tiling_rule(pt):
 
 
 def test_argument_validation(pt):
-    for bad in (dict(width=0), dict(depth=0), dict(sphere_count=0), dict(sphere_count=2000, sphere_stride=2000), dict(sphere_stride=4)):
+    # depth: the kernels keep a path's bounce count in 24 bits of the lane's state word (csrc/trace_kernels.cu)
+    for bad in (dict(width=0), dict(depth=0), dict(depth=1 << 24), dict(sphere_count=0), dict(sphere_count=2000, sphere_stride=2000),
+                dict(sphere_stride=4)):
         with pytest.raises(pt.PtError) as ei:
             pt.render_do_ex(pt.default_params(**bad), 16, 32, 48, stream=0)
         assert ei.value.code == -1
