@@ -594,9 +594,10 @@ int ptb200::render_host_slice(const char *who, const PtParams *p, const float *r
     // Chunked so that the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap
     // (three engines, three streams).  With pinned host memory the copies are truly asynchronous.
     constexpr int kStreams = 4;
-    static const int64_t chunk_paths = env_ll("PTB200_HOST_CHUNK", 8LL << 20, 1024);  // experiments only; below 1024 is ignored
-    // Peak paths per chunk: 192 MiB in, 96 MiB out.  Measured on C2 (1.2 GB in, 0.6 GB out) with the ramped schedule below:
-    // 4 Mi 25.9 ms, 8 Mi 25.1, 16 Mi 25.0, 32 Mi 25.1; equal 4 Mi chunks without the ramps 26.7 ms.  The link itself moves
+    static const int64_t chunk_paths = env_ll("PTB200_HOST_CHUNK", 16LL << 20, 1024);  // experiments only; below 1024 is ignored
+    // Peak paths per chunk: 384 MiB in, 192 MiB out.  Measured on C2 (1.2 GB in, 0.6 GB out) with the ramped schedule below
+    // (tools/e2e_ramp_ab.py, median of 9 calls): peak 8 Mi, ramps from peak/8: 25.1 ms; from peak/32: 25.0; from peak/128: 25.2;
+    // peak 16 Mi from peak/64: 24.9; peak 4 Mi from peak/32: 26.0; equal 4 Mi chunks without ramps 26.7 ms.  The link itself moves
     // the same bytes in 23.0 ms as two giant copies (52.5 GB/s in while 26.3 GB/s go out, tools/pcie_probe.py).
     int64_t chunk = chunk_paths;
     if (chunk > n)
@@ -629,11 +630,12 @@ int ptb200::render_host_slice(const char *who, const PtParams *p, const float *r
             e = cudaStreamWaitEvent(st[b], sph_ready, 0);
         PtParams cp = *p;
         // Chunk schedule: the first chunk's upload and the last chunk's kernel + download overlap with nothing, so the
-        // schedule ramps up from chunk/8 and down again to chunk/8 (3 ms of exposed transfer with equal chunks on C2, 0.4 ms so).
+        // schedule ramps up from chunk/64 and down again to chunk/64 (3 ms of exposed transfer with equal chunks on C2, 0.1 ms so).
         std::vector<int64_t> sizes;
         {
-            // peak chunk: the largest chunk / 2^j whose two ramps (chunk/8 ... peak/2 each) take at most half of the job
-            int64_t peak = chunk, first_c = chunk / 8 < 1024 ? chunk : chunk / 8;
+            // peak chunk: the largest chunk / 2^j whose two ramps (chunk/64 ... peak/2 each) take at most half of the job
+            static const int64_t ramp_div = env_ll("PTB200_HOST_RAMP", 64, 1);  // experiments only
+            int64_t peak = chunk, first_c = chunk / ramp_div < 1024 ? chunk : chunk / ramp_div;
             while (peak > first_c && 2 * (peak - first_c) > n / 2)
                 peak /= 2;
             int64_t left = n;
