@@ -26,4 +26,4 @@ for _ in range(9):
     t = time.perf_counter()
     pt.render_host(p, h_rays, sph, h_col)
     ts.append((time.perf_counter() - t) * 1e3)
-print(f"ramp {os.environ.get('PTB200_HOST_RAMP', '8')} chunk {os.environ.get('PTB200_HOST_CHUNK', 'default')}: best {min(ts):.3f} median {np.median(ts):.3f} ms")
+print(f"ramp {os.environ.get('PTB200_HOST_RAMP', 'default')} chunk {os.environ.get('PTB200_HOST_CHUNK', 'default')}: best {min(ts):.3f} median {np.median(ts):.3f} ms")
