@@ -477,6 +477,9 @@ def main():
         e2e["link"] = {"copies_only_ms": l_ms, "aggregate_gbs": 36 * n * world / (l_ms * 1e-3) / 1e9, "e2e_aggregate_gbs": 36 * n * world / (e_ms * 1e-3) / 1e9,
                        "what": "all ranks at once: H2D of the rank's rays and D2H of its colours as two concurrent pinned copies, no kernel (best of 2)"}
         e2e["frac_of_link"] = l_ms / e_ms
+        e2e["frac_of_link_note"] = ("copies-only time / e2e time: how close the chunked upload-trace-download pipeline comes to moving the same bytes with no "
+                                    "kernel at all; above 1 when several ranks share one host and two giant copies per rank use the host's memory system "
+                                    "worse than the pipeline's interleaved chunks do")
         e2e["host_numa"] = numa
         del h_rays, h_col
         # The whole run.sh-equivalent pipeline through one C-ABI call: scene (512 B, host) in, 8-bit stripe (host) out;
