@@ -184,6 +184,9 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
     unsigned int issued, head;
     unsigned int scratch;                // FUSE: index of this warp's colour scratch in c_fuse.scratch
     bool postponed;                      // FUSE: a chunk claim is waiting for a straggler (warp-uniform)
+#ifdef PTB_TEST_POSTPONE
+    unsigned int test_postponements = 0u;
+#endif
 
     // GEN: rays are generated straight into the ring (c_gen) and never exist in HBM; pl.ray is unused then.
     __device__ __forceinline__ PathFeeder(const TracePlanes &planes, float *ring_, unsigned long long *counter_, unsigned int count_,
@@ -230,7 +233,16 @@ template <bool GEN, bool FUSE = false> struct PathFeeder {
                 // postpones the claim: take() hands out nothing beyond what was issued, lanes that find the ring dry go idle, and
                 // the warp tries again at its next swap (there is one: the straggler's own).  In practice the ring's four
                 // batches outlast any path (depth 50: ~55 iterations of supply).
-                if (__any_sync(0xffffffffu, holds && held_seq < (issued - kChunkBatches) * 32u)) {
+                bool straggler = __any_sync(0xffffffffu, holds && held_seq < (issued - kChunkBatches) * 32u);
+#ifdef PTB_TEST_POSTPONE  // test build: every other claim is postponed three times although nothing straggles (dry ring, re-arm)
+                if (!straggler && ((issued / kChunkBatches) & 1u) == 0u && test_postponements < 3u) {
+                    test_postponements++;
+                    straggler = true;
+                } else if (!straggler) {
+                    test_postponements = 0u;
+                }
+#endif
+                if (straggler) {
                     postponed = true;
                     return false;
                 }

@@ -6,6 +6,10 @@
 set -e
 cd "$(dirname "$0")/.."
 python -c "from ascendpathtracing_b200 import build as b; print(b.build_variant('checked', ['PTB_CHECKED']))"
+# second build: the fused resolve's rarely taken path -- a chunk claim postponed behind a straggling path, the ring running dry,
+# idle lanes re-armed -- forced on every other claim (-DPTB_TEST_POSTPONE), asserts on; the fused images must not change
+python -c "from ascendpathtracing_b200 import build as b; print(b.build_variant('postpone', ['PTB_TEST_POSTPONE', 'PTB_CHECKED']))"
 if python -c "import torch, sys; sys.exit(0 if torch.cuda.is_available() else 1)"; then
     PTB200_LIB=$PWD/ascendpathtracing_b200/libptb200_checked.so python -m pytest tests -m gpu -q "$@"
+    PTB200_LIB=$PWD/ascendpathtracing_b200/libptb200_postpone.so python -m pytest tests/test_gpu_fused_resolve.py -m gpu -q
 fi
