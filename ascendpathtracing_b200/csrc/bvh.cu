@@ -1,7 +1,6 @@
 // GPU build of the sphere BVH of pt_bvh.cuh (LBVH: Morton codes -> radix sort -> Karras 2012 hierarchy -> bottom-up
-// boxes), plus the C-ABI handle around it.  The only library call is cub::DeviceRadixSort for the one-time sort of the
-// Morton keys; everything on the per-ray path (traversal, leaf tests) is this repo's code.
-#include <cub/device/device_radix_sort.cuh>
+// boxes), plus the C-ABI handle around it.  No library calls: the one-time sort of the Morton keys is the small stable LSD
+// radix sort below (round 1 called cub::DeviceRadixSort here).
 
 #include <algorithm>
 #include <cmath>
@@ -27,6 +26,121 @@ struct MortonPlan {
     unsigned char axis[kKeyBits];
     int nbits[3];  // bits each axis receives in total
 };
+
+// ---- stable LSD radix sort of (30-bit key, int value) pairs: three passes of 10 bits ------------------------------------
+// One warp owns one tile of consecutive elements.  Pass = count (per-tile histogram) -> scan (exclusive prefix over
+// [bin][tile], one block) -> scatter (the warp walks its tile 32 elements at a time IN ORDER; lanes with the same digit are
+// ranked by lane with match.any, the lowest of them bumps the tile's running offset for that digit), which keeps equal keys
+// in input order like any LSD radix sort must.  Sized for a one-time build of 10^4 .. 10^7 keys, not for throughput.
+constexpr int kRadixBits = 10, kRadixBins = 1 << kRadixBits, kRadixPasses = 3;
+static_assert(kRadixBits * kRadixPasses >= kKeyBits, "the passes must cover the key");
+
+__global__ void __launch_bounds__(32) radix_count_kernel(const unsigned int *__restrict__ keys, int n, int tile, int shift, unsigned int *hist,
+                                                         int n_tiles) {
+    __shared__ unsigned int cnt[kRadixBins];
+    const int lane = threadIdx.x, t = blockIdx.x;
+    for (int b = lane; b < kRadixBins; b += 32)
+        cnt[b] = 0u;
+    __syncwarp();
+    const int t0 = t * tile, t1 = min(n, t0 + tile);
+    for (int i = t0 + lane; i < t1; i += 32)
+        atomicAdd(&cnt[(keys[i] >> shift) & (kRadixBins - 1)], 1u);
+    __syncwarp();
+    for (int b = lane; b < kRadixBins; b += 32)
+        hist[static_cast<size_t>(b) * n_tiles + t] = cnt[b];
+}
+
+// exclusive prefix sum of hist[0 .. m) in place, one block of 1024 threads
+__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned int *hist, int m) {
+    __shared__ unsigned int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (m + 1023) / 1024, a = tid * per, b = min(m, a + per);
+    unsigned int sum = 0u;
+    for (int i = a; i < b; i++)
+        sum += hist[i];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+        const unsigned int v = tid >= o ? part[tid - o] : 0u;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    unsigned int run = part[tid] - sum;  // exclusive
+    for (int i = a; i < b; i++) {
+        const unsigned int v = hist[i];
+        hist[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(32) radix_scatter_kernel(const unsigned int *__restrict__ keys_in, const int *__restrict__ vals_in, int n, int tile,
+                                                           int shift, const unsigned int *__restrict__ hist, int n_tiles, unsigned int *keys_out,
+                                                           int *vals_out) {
+    __shared__ unsigned int base[kRadixBins];
+    const int lane = threadIdx.x, t = blockIdx.x;
+    for (int b = lane; b < kRadixBins; b += 32)
+        base[b] = hist[static_cast<size_t>(b) * n_tiles + t];
+    __syncwarp();
+    unsigned int lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    const int t0 = t * tile, t1 = min(n, t0 + tile);
+    for (int c = t0; c < t1; c += 32) {  // warp-uniform
+        const int i = c + lane;
+        const bool valid = i < t1;
+        const unsigned int key = valid ? keys_in[i] : 0u;
+        const int val = valid ? vals_in[i] : 0;
+        const unsigned int d = valid ? ((key >> shift) & (kRadixBins - 1)) : static_cast<unsigned int>(kRadixBins + lane);  // no peers
+        const unsigned int peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned int off = 0u;
+        if (valid && lane == leader) {
+            off = base[d];
+            base[d] = off + __popc(peers);
+        }
+        off = __shfl_sync(0xffffffffu, off, leader);
+        if (valid) {
+            const unsigned int dst = off + __popc(peers & lt);
+            keys_out[dst] = key;
+            vals_out[dst] = val;
+        }
+        __syncwarp();
+    }
+}
+
+struct RadixPlan {
+    int tile, n_tiles;
+    size_t hist_bytes;
+};
+static RadixPlan radix_plan(int n) {
+    RadixPlan p;
+    int tile = (n + 511) / 512;            // at most 512 tiles (the one-block scan walks bins x tiles entries per pass) ...
+    tile = (tile + 31) / 32 * 32;
+    p.tile = tile < 256 ? 256 : tile;      // ... of at least 256 elements
+    p.n_tiles = (n + p.tile - 1) / p.tile;
+    p.hist_bytes = sizeof(unsigned int) * kRadixBins * static_cast<size_t>(p.n_tiles);
+    return p;
+}
+
+// keys_a / vals_a (input, clobbered) -> keys_b / vals_b (sorted): an odd number of passes ends in the b buffers
+static cudaError_t radix_sort_pairs(cudaStream_t stream, unsigned int *keys_a, int *vals_a, unsigned int *keys_b, int *vals_b, int n, unsigned int *hist) {
+    static_assert(kRadixPasses % 2 == 1, "the result must land in the b buffers");
+    const RadixPlan p = radix_plan(n);
+    for (int pass = 0; pass < kRadixPasses; pass++) {
+        const int shift = pass * kRadixBits;
+        const unsigned int *ki = (pass & 1) ? keys_b : keys_a;
+        const int *vi = (pass & 1) ? vals_b : vals_a;
+        unsigned int *ko = (pass & 1) ? keys_a : keys_b;
+        int *vo = (pass & 1) ? vals_a : vals_b;
+        radix_count_kernel<<<p.n_tiles, 32, 0, stream>>>(ki, n, p.tile, shift, hist, p.n_tiles);
+        radix_scan_kernel<<<1, 1024, 0, stream>>>(hist, kRadixBins * p.n_tiles);
+        radix_scatter_kernel<<<p.n_tiles, 32, 0, stream>>>(ki, vi, n, p.tile, shift, hist, p.n_tiles, ko, vo);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return e;
+    }
+    return cudaSuccess;
+}
 
 // AoS copies of the per-sphere data (original index order) + Morton keys of the small spheres.
 __global__ void prepare_kernel(const float *__restrict__ sph, int n, int stride, float4 *geom, float4 *color, float4 *emission, const int *small_index,
@@ -367,15 +481,12 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
                  o_emis = carve(keep_bytes, sizeof(float4) * count), o_big = carve(keep_bytes, sizeof(int) * std::max(nb, 1)),
                  o_soa = carve(keep_bytes, sizeof(float) * 11 * 1024), o_qn = carve(keep_bytes, sizeof(QNode) * nn1),
                  o_small = carve(keep_bytes, sizeof(int) * ns1);
-    size_t cub_bytes = 0;
-    if (ns >= 2)  // size query only: no pointer is touched
-        e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<const unsigned int *>(nullptr), static_cast<unsigned int *>(nullptr),
-                                            static_cast<const int *>(nullptr), static_cast<int *>(nullptr), ns, 0, kKeyBits, stream);
+    const size_t hist_bytes = ns >= 2 ? radix_plan(ns).hist_bytes : 0;  // the sort's histogram
     const size_t o_nodes = carve(temp_bytes, sizeof(BvhNode) * nn1), o_keys_in = carve(temp_bytes, sizeof(unsigned int) * ns1),
                  o_keys = carve(temp_bytes, sizeof(unsigned int) * ns1), o_vals_in = carve(temp_bytes, sizeof(int) * ns1),
                  o_vals = carve(temp_bytes, sizeof(int) * ns1), o_parent = carve(temp_bytes, sizeof(int) * ns1),
                  o_visits = carve(temp_bytes, sizeof(unsigned int) * ns1), o_own = carve(temp_bytes, sizeof(Aabb) * ns1),
-                 o_cub = carve(temp_bytes, cub_bytes ? cub_bytes : 16);
+                 o_hist = carve(temp_bytes, hist_bytes ? hist_bytes : 16);
     char *keep = nullptr, *temp = nullptr;
     WsBlock ws;
     if (e == cudaSuccess)
@@ -407,7 +518,7 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
     int *const d_leaf_parent = reinterpret_cast<int *>(temp + o_parent);
     unsigned int *const d_visits = reinterpret_cast<unsigned int *>(temp + o_visits);
     Aabb *const d_own = reinterpret_cast<Aabb *>(temp + o_own);
-    void *const d_tmp = temp + o_cub;
+    void *const d_tmp = temp + o_hist;
     int *const d_small = b->small_index;
     if (e == cudaSuccess && nb > 0)
         e = cudaMemcpyAsync(b->big_index, big.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, stream);
@@ -429,8 +540,7 @@ int ptb200_bvh_build(const uint8_t *spheres_, int32_t count, int32_t stride, voi
         b->only_leaf = ~small[0];
     }
     if (e == cudaSuccess && ns >= 2) {
-        size_t tmp_bytes = cub_bytes;
-        e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys_in, d_keys, d_vals_in, d_vals, ns, 0, kKeyBits, stream);
+        e = radix_sort_pairs(stream, d_keys_in, d_vals_in, d_keys, d_vals, ns, static_cast<unsigned int *>(d_tmp));
         if (e == cudaSuccess)
             e = cudaMemsetAsync(d_visits, 0, sizeof(unsigned int) * ns, stream);
         if (e == cudaSuccess) {
