@@ -156,17 +156,21 @@ __device__ __forceinline__ void generate_ray(const RayGenSource &g, long long i,
     const RayGenArgs &a = g.a;
     // global path index ((((x*H + y)*2 + sy)*2 + sx)*S + k), gen_data.py:32-36
     int sx, sy, x, y;
+    uint64_t gp = static_cast<uint64_t>(g.path0 + i);  // global path index = RNG counter (a strided launch: set below)
     if (g.fast_index) {  // no 64-bit divisions
         const unsigned int spp = 4u * static_cast<unsigned int>(a.s);
         const unsigned int ii = static_cast<unsigned int>(i);
         const unsigned int lp = a.by_spp.div(ii);
         const unsigned int pix = g.pix_base + lp;
-        const unsigned int sub = a.by_s.div(ii - lp * spp);
+        const unsigned int rest = ii - lp * spp;
+        const unsigned int sub = a.by_s.div(rest);
         sx = static_cast<int>(sub & 1u);
         sy = static_cast<int>(sub >> 1);
         x = static_cast<int>(a.by_h.div(pix));
         y = static_cast<int>(pix - static_cast<unsigned int>(x) * static_cast<unsigned int>(a.ih));
         x = g.x_first + x * g.x_step;  // dense column -> image column (identity unless strided)
+        if (g.x_step > 1)              // the strided launch's global index from the decode above (== strided_global_path(g, i))
+            gp = (static_cast<uint64_t>(static_cast<unsigned int>(x)) * static_cast<unsigned int>(a.ih) + static_cast<unsigned int>(y)) * spp + rest;
     } else {
         long long r = (g.path0 + i) / a.s;
         sx = static_cast<int>(r & 1);
@@ -184,7 +188,6 @@ __device__ __forceinline__ void generate_ray(const RayGenSource &g, long long i,
         // rand() = ((a >> 5) * 2^26 + (b >> 6)) / 2^53 = m / 2^53 with the 53-bit integer m = (a >> 5) << 26 | (b >> 6): the sum
         // and the division are exact in binary64, and so is the doubling: 2 * rand() = m * 2^-52.  One integer conversion and
         // one exact scaling replace two conversions, a multiply, an add, a divide and the doubling -- same bits.
-        const uint64_t gp = g.x_step > 1 ? strided_global_path(g, static_cast<unsigned int>(i)) : static_cast<uint64_t>(g.path0 + i);
         uint32_t c[4] = {static_cast<uint32_t>(gp), static_cast<uint32_t>(gp >> 32), 0u, 0u};
         philox4x32_10_keyed(c, g.keys);
         const unsigned long long m1 = (static_cast<unsigned long long>(c[0] >> 5) << 26) | (c[1] >> 6);
